@@ -1,0 +1,171 @@
+/*
+ * p3p.h -- C ABI of libp3p.so: the B200 (sm_100a) LiDAR pillar-encode +
+ * early-fusion hot path of PixelsPointsPolygons.
+ *
+ * Plain C: device pointers, sizes, a CUDA stream handle passed as void*.
+ * No allocation, no host synchronisation and no host<->device copy happens
+ * inside any p3p_* compute call; the caller owns every buffer (workspace
+ * included) and the stream.  All device pointers must be 16-byte aligned.
+ * Every function returns 0 on success or a negative P3P_ERR_* code;
+ * p3p_last_error() gives the message of the last failure on this thread.
+ *
+ * What each entry point replaces in the reference (R: = /root/reference):
+ *
+ *   p3p_voxelize          R:pixelspointspolygons/models/pointpillars/pointpillars_o3d.py:92
+ *                         `self.voxelize(x_lidar)` = Open3D-ML PointPillars.voxelize ->
+ *                         PointPillarsVoxelization.forward -> open3d.ml.torch.ops.voxelize +
+ *                         ragged_to_dense + x/y bound filter, for the
+ *                         whole jagged batch in one call instead of a Python loop per tile.
+ *   p3p_pfn_prepare       folds the eval-mode BatchNorm1d of the two PFNLayers into the linears
+ *                         (Open3D-ML PFNLayer; state_dict keys of SURVEY Appendix C) and packs the
+ *                         second linear in the tensor-core operand layout.
+ *   p3p_pillar_features   pointpillars_o3d.py:93 `self.voxel_encoder(voxels, num_points, coors)`
+ *                         (PillarFeatureNet.forward, rows a6, a7) -> (V, C) in voxel order.
+ *   p3p_encode            pointpillars_o3d.py:92-107: voxelize -> voxel_encoder -> middle_encoder
+ *                         (PointPillarsScatter, row a8) -> NCHW or NLC, optionally straight into the
+ *                         LiDAR half of the early-fusion concat buffer
+ *                         (R:pixelspointspolygons/models/fusion_layers/early_fusion_vit.py:100,113-121,
+ *                         rows a10, a11).
+ *   p3p_patch_embed       early_fusion_vit.py:99 `self.image_embed(x_image)` (timm PatchEmbed conv
+ *                         PxP/P, flatten=False, row a9), written into the image half of the concat
+ *                         buffer (early_fusion_vit.py:121 puts image channels first).
+ */
+#ifndef P3P_H_
+#define P3P_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3P_VERSION 100
+
+enum {
+    P3P_OK = 0,
+    P3P_ERR_INVALID_ARGUMENT = -1, /* null / misaligned pointer, bad size or enum */
+    P3P_ERR_UNSUPPORTED = -2,      /* configuration outside what the kernels implement */
+    P3P_ERR_WORKSPACE = -3,        /* workspace too small */
+    P3P_ERR_CUDA = -4              /* a CUDA runtime call failed (message has the detail) */
+};
+
+/* Arithmetic of the second PFN linear (the dense 32 -> C contraction). */
+enum {
+    P3P_PRECISION_FP32 = 0, /* exact fp32 FMA on CUDA cores (any M; slow; GPU-side cross-check) */
+    P3P_PRECISION_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate -- the fp32 (1e-3) contract */
+    P3P_PRECISION_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate -- the bf16 (1e-2) contract */
+};
+
+/* Output tensor layouts of p3p_encode. */
+enum {
+    P3P_LAYOUT_NCHW = 0, /* (B, c_total, ny, nx), LiDAR channels at [c_offset, c_offset + C) */
+    P3P_LAYOUT_NLC = 1   /* (B, ny*nx, C) contiguous tokens == x.flatten(2).transpose(1,2) values */
+};
+
+enum { P3P_DTYPE_F32 = 0, P3P_DTYPE_BF16 = 1 };
+
+/*
+ * Voxel grid and limits.  Mirrors the constructor arguments the reference derives from
+ * cfg.experiment.encoder.* (pointpillars_o3d.py:39-47) plus PointPillarsScatter's output_shape
+ * (R:pixelspointspolygons/models/pointpillars/pointpillars_vit.py:55,60-63).
+ */
+typedef struct p3p_grid {
+    float range_min[3];  /* point_cloud_range[:3]  (0, 0, 0) */
+    float range_max[3];  /* point_cloud_range[3:]  (in_width, in_height, in_voxel_size.z) */
+    float voxel_size[3]; /* in_voxel_size.{x,y,z} */
+    int32_t max_points;  /* max_num_points_per_voxel (M) */
+    int32_t max_voxels;  /* max_num_voxels.{train|test} -- the caller picks by module mode */
+    int32_t ny, nx;      /* scatter output_shape = [ny, nx] */
+    int32_t flags;       /* 0, or P3P_GRID_DROP_OVERFLOW */
+} p3p_grid;
+
+/* Points whose cell hash is >= extents_x*extents_y*extents_z (they sit exactly on range_max: z == 100
+ * -> z-cell 1, y == 224 -> y-cell 28) are ordinary runs by default; with this
+ * flag they are dropped like out-of-range points (the other reading of Open3D's invalid_hash guard). */
+#define P3P_GRID_DROP_OVERFLOW 1
+
+/* Raw (un-folded) eval-mode parameters of the PillarFeatureNet, fp32 device pointers.
+ * Names are the reference's state_dict keys under `voxel_encoder.pfn_layers.{0,1}.`. */
+typedef struct p3p_pfn_params {
+    const float* linear0_weight; /* (C0, 8)   pfn_layers.0.linear.weight, C0 = feat_channels[0] / 2 = 32 */
+    const float* norm0_weight;   /* (C0)      pfn_layers.0.norm.weight */
+    const float* norm0_bias;     /* (C0) */
+    const float* norm0_mean;     /* (C0)      running_mean */
+    const float* norm0_var;      /* (C0)      running_var */
+    const float* linear1_weight; /* (C, 2*C0) pfn_layers.1.linear.weight */
+    const float* norm1_weight;   /* (C) */
+    const float* norm1_bias;     /* (C) */
+    const float* norm1_mean;     /* (C) */
+    const float* norm1_var;      /* (C) */
+    float eps;                   /* BatchNorm1d eps (1e-3) */
+    int32_t channels;            /* C = feat_channels[1] = patch_feature_dim (384) */
+    int32_t center_alias;        /* 1: channels 0,1 hold the pillar-centre offsets */
+} p3p_pfn_params;
+
+/* Optional integer outputs of p3p_voxelize (the bit-exact parity surface).  Any pointer may be
+ * NULL.  All arrays are padded per tile to max_voxels rows; rows >= num_pillars[b] are untouched. */
+typedef struct p3p_voxel_outputs {
+    int32_t* point_hash;       /* (total_points) cell hash per point, invalid_hash (= number of keys) when out of range */
+    int32_t* num_pillars;      /* (B) pillars per tile after the max_voxels cut and the x/y bound filter */
+    int32_t* pillar_coords;    /* (B, max_voxels, 4) [b, z, y, x] in voxel order */
+    int32_t* pillar_num_points;/* (B, max_voxels) min(count, M) */
+    int32_t* pillar_point_idx; /* (B, max_voxels, M) tile-local point indices, ascending, -1 padded */
+    float* pillar_points;      /* (B, max_voxels, M, 3) gathered xyz, zero padded (== `voxels`) */
+    int32_t* cell_owner;       /* (B, ny*nx) voxel ordinal that owns each canvas cell (last writer), -1 if empty */
+} p3p_voxel_outputs;
+
+const char* p3p_last_error(void);
+int p3p_version(void);
+
+/* Bytes of scratch the compute calls need for a batch of B tiles holding total_points points. */
+size_t p3p_workspace_bytes(const p3p_grid* grid, int32_t num_tiles, int64_t total_points);
+
+/* Bytes of the prepared-weights blob for C output channels. */
+size_t p3p_pfn_blob_bytes(int32_t channels);
+
+/* Fold BN into the linears and pack for `precision`; writes `blob` (device). */
+int p3p_pfn_prepare(const p3p_pfn_params* params, int32_t precision, void* blob, size_t blob_bytes, void* stream);
+
+/*
+ * Voxelise a jagged batch.  points: (total_points, point_stride) fp32, xyz in lanes 0..2;
+ * tile_offsets: (B + 1) int64 on the device (NestedTensor jagged offsets, or arange * N for dense).
+ * Leaves the pillar table of the batch in `workspace` for p3p_pillar_features.
+ */
+int p3p_voxelize(const float* points, int32_t point_stride, const int64_t* tile_offsets, int32_t num_tiles,
+                 int64_t total_points, const p3p_grid* grid, const p3p_voxel_outputs* out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * PillarFeatureNet over the pillar table left in `workspace` by p3p_voxelize (same stream, same
+ * num_tiles / total_points): features (B, max_voxels, C) fp32, rows >= num_pillars[b] untouched.
+ */
+int p3p_pillar_features(const p3p_grid* grid, int32_t num_tiles, int64_t total_points, const void* blob,
+                        int32_t channels, int32_t precision, float* features, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/*
+ * The fused hot path: voxelize -> PFN -> scatter, one call per batch.
+ * out: NCHW (B, c_total, ny, nx) written at channels [c_offset, c_offset + C), or NLC (B, ny*nx, C)
+ * (c_total / c_offset ignored).  Every cell of the LiDAR channels is written (empty cells = 0), so the
+ * buffer needs no memset.  lidar_zero != 0 reproduces `x_lidar * 0.0` (LiDAR dropout) without running
+ * the encoder.
+ */
+int p3p_encode(const float* points, int32_t point_stride, const int64_t* tile_offsets, int32_t num_tiles,
+               int64_t total_points, const p3p_grid* grid, const void* blob, int32_t channels, int32_t precision,
+               void* out, int32_t out_layout, int32_t out_dtype, int32_t c_total, int32_t c_offset,
+               int32_t lidar_zero, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Image patch embedding: Conv2d(in_chans, C, kernel=P, stride=P, bias) on (B, in_chans, H, W) fp32,
+ * written NCHW into channels [c_offset, c_offset + C) of out (B, c_total, H/P, W/P).
+ * weight: (C, in_chans, P, P) fp32; bias: (C) fp32 or NULL.
+ */
+int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, int32_t height, int32_t width,
+                    int32_t patch, const float* weight, const float* bias, int32_t channels, int32_t precision,
+                    void* out, int32_t out_dtype, int32_t c_total, int32_t c_offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3P_H_ */

@@ -1,0 +1,8 @@
+"""pixelspointspolygons_b200 -- B200 (sm_100a) LiDAR pillar-encode + early-fusion hot path of PixelsPointsPolygons.
+
+Host side mirrors the reference's encoder plugin interface; the compute is libp3p.so (include/p3p.h).
+"""
+from .config import AttrDict, default_cfg  # noqa: F401
+from .encoder import PointPillarsEncoder  # noqa: F401
+
+__all__ = ["AttrDict", "default_cfg", "PointPillarsEncoder"]

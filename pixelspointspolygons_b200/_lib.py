@@ -1,0 +1,93 @@
+"""ctypes binding of libp3p.so (include/p3p.h).  No torch types cross this boundary: device pointers are
+passed as integers, the CUDA stream as a void*."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+P3P_PRECISION = {"fp32": 0, "tf32": 1, "bf16": 2}
+P3P_LAYOUT_NCHW, P3P_LAYOUT_NLC = 0, 1
+P3P_DTYPE_F32, P3P_DTYPE_BF16 = 0, 1
+P3P_GRID_DROP_OVERFLOW = 1
+
+EXPORTED = [
+    "p3p_last_error", "p3p_version", "p3p_workspace_bytes", "p3p_pfn_blob_bytes", "p3p_pfn_prepare",
+    "p3p_voxelize", "p3p_pillar_features", "p3p_encode", "p3p_patch_embed",
+]
+
+
+class Grid(C.Structure):
+    _fields_ = [("range_min", C.c_float * 3), ("range_max", C.c_float * 3), ("voxel_size", C.c_float * 3),
+                ("max_points", C.c_int32), ("max_voxels", C.c_int32), ("ny", C.c_int32), ("nx", C.c_int32),
+                ("flags", C.c_int32)]
+
+
+class PfnParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "linear0_weight", "norm0_weight", "norm0_bias", "norm0_mean", "norm0_var",
+        "linear1_weight", "norm1_weight", "norm1_bias", "norm1_mean", "norm1_var")] + [
+        ("eps", C.c_float), ("channels", C.c_int32), ("center_alias", C.c_int32)]
+
+
+class VoxelOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "point_hash", "num_pillars", "pillar_coords", "pillar_num_points", "pillar_point_idx", "pillar_points",
+        "cell_owner")]
+
+
+class P3PError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Fails loudly when it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise P3PError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `python -m pixelspointspolygons_b200.build`). This package has no CPU or eager fallback.")
+    l = C.CDLL(LIB_PATH)
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    l.p3p_last_error.restype = C.c_char_p
+    l.p3p_last_error.argtypes = []
+    l.p3p_version.restype = C.c_int
+    l.p3p_version.argtypes = []
+    l.p3p_workspace_bytes.restype = sz
+    l.p3p_workspace_bytes.argtypes = [C.POINTER(Grid), i32, i64]
+    l.p3p_pfn_blob_bytes.restype = sz
+    l.p3p_pfn_blob_bytes.argtypes = [i32]
+    l.p3p_pfn_prepare.restype = C.c_int
+    l.p3p_pfn_prepare.argtypes = [C.POINTER(PfnParams), i32, vp, sz, vp]
+    l.p3p_voxelize.restype = C.c_int
+    l.p3p_voxelize.argtypes = [vp, i32, vp, i32, i64, C.POINTER(Grid), C.POINTER(VoxelOutputs), vp, sz, vp]
+    l.p3p_pillar_features.restype = C.c_int
+    l.p3p_pillar_features.argtypes = [C.POINTER(Grid), i32, i64, vp, i32, i32, vp, vp, sz, vp]
+    l.p3p_encode.restype = C.c_int
+    l.p3p_encode.argtypes = [vp, i32, vp, i32, i64, C.POINTER(Grid), vp, i32, i32, vp, i32, i32, i32, i32, i32, vp, sz, vp]
+    l.p3p_patch_embed.restype = C.c_int
+    l.p3p_patch_embed.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp]
+    _lib = l
+    return l
+
+
+def check(rc: int, what: str = "p3p call"):
+    if rc != 0:
+        msg = lib().p3p_last_error().decode("utf-8", "replace")
+        raise P3PError(f"{what} failed (code {rc}): {msg}")
+
+
+def make_grid(range_min, range_max, voxel_size, max_points, max_voxels, ny, nx, flags=0) -> Grid:
+    g = Grid()
+    for i in range(3):
+        g.range_min[i] = float(range_min[i])
+        g.range_max[i] = float(range_max[i])
+        g.voxel_size[i] = float(voxel_size[i])
+    g.max_points, g.max_voxels, g.ny, g.nx, g.flags = int(max_points), int(max_voxels), int(ny), int(nx), int(flags)
+    return g

@@ -1,0 +1,285 @@
+// capi.cu -- extern "C" entry points of libp3p.so (declared in include/p3p.h).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "p3p_internal.cuh"
+
+namespace p3p {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            sms = n;
+        else
+            sms = 148;  // B200; keeps p3p_workspace_bytes usable on a box without a GPU
+        (void)cudaGetLastError();
+    }
+    return sms;
+}
+
+// Same fp32 operation sequence as Open3D VoxelizeCPU / PointPillarsVoxelization.
+int make_grid(const p3p_grid* g, GridDev* out) {
+    if (!g) return fail(P3P_ERR_INVALID_ARGUMENT, "grid is null");
+    GridDev d;
+    memset(&d, 0, sizeof(d));
+    for (int i = 0; i < 3; ++i) {
+        if (!(g->voxel_size[i] > 0.f) || !(g->range_max[i] > g->range_min[i]))
+            return fail(P3P_ERR_INVALID_ARGUMENT, "grid axis %d: voxel_size must be > 0 and range_max > range_min", i);
+        d.mn[i] = g->range_min[i];
+        d.mx[i] = g->range_max[i];
+        volatile float inv = 1.0f / g->voxel_size[i];
+        d.inv[i] = inv;
+        volatile float span = g->range_max[i] - g->range_min[i];
+        volatile float cells = span * inv;
+        d.ext[i] = (int)ceilf(cells);
+        volatile float q = span / g->voxel_size[i];
+        d.nv[i] = (int)q;
+        if (d.ext[i] < 1 || d.ext[i] > 1023) return fail(P3P_ERR_UNSUPPORTED, "grid axis %d: %d cells (supported: 1..1023)", i, d.ext[i]);
+    }
+    d.stride1 = d.ext[0];
+    d.stride2 = d.ext[0] * d.ext[1];
+    const long long cells = (long long)d.stride2 * d.ext[2];
+    const long long keys = (long long)d.ext[0] + (long long)d.ext[1] * d.stride1 + (long long)d.ext[2] * d.stride2 + 1;
+    d.flags = g->flags;
+    d.num_cells = (int)cells;
+    const long long nkeys = (g->flags & P3P_GRID_DROP_OVERFLOW) ? cells : keys;
+    if (nkeys > kMaxKeys)
+        return fail(P3P_ERR_UNSUPPORTED, "%lld pillar keys exceed the shared-memory ranking budget (%d)", nkeys, kMaxKeys);
+    d.num_keys = (int)nkeys;
+    if (g->max_points < 1 || g->max_points > 1024) return fail(P3P_ERR_UNSUPPORTED, "max_points %d (supported: 1..1024)", g->max_points);
+    if (g->max_voxels < 1) return fail(P3P_ERR_INVALID_ARGUMENT, "max_voxels %d", g->max_voxels);
+    d.M = g->max_points;
+    d.Vmax = g->max_voxels;
+    d.ny = g->ny;
+    d.nx = g->nx;
+    // PointPillarsScatter writes canvas[:, y * nx + x]; the pillar filter bounds y < nv[1], x < nv[0].
+    if (d.ny < d.nv[1] || d.nx < d.nv[0] || d.ny < 1 || d.nx < 1)
+        return fail(P3P_ERR_INVALID_ARGUMENT, "scatter output_shape (%d, %d) smaller than the voxel grid (%d, %d)", d.ny, d.nx, d.nv[1], d.nv[0]);
+    d.vx = g->voxel_size[0];
+    d.vy = g->voxel_size[1];
+    d.x_off = g->voxel_size[0] / 2 + g->range_min[0];
+    d.y_off = g->voxel_size[1] / 2 + g->range_min[1];
+    *out = d;
+    return P3P_OK;
+}
+
+int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out) {
+    if (B < 0 || total_points < 0) return fail(P3P_ERR_INVALID_ARGUMENT, "negative batch or point count");
+    WsLayout l;
+    memset(&l, 0, sizeof(l));
+    l.B = B;
+    const int target = 3 * device_sm_count();
+    int64_t denom = target - B;
+    if (denom < 64) denom = 64;
+    int64_t S = (total_points + denom - 1) / denom;
+    S = (S + 255) / 256 * 256;
+    if (S < 1024) S = 1024;
+    if (S > 8192) S = 8192;
+    l.chunk_points = (int)S;
+    const int64_t mc = total_points / S + B;
+    if (mc > 0x7fffffff) return fail(P3P_ERR_UNSUPPORTED, "too many ranking chunks");
+    l.max_chunks = (int)mc;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t HW = (size_t)g.ny * g.nx;
+    l.off_chunk_hist = take((size_t)l.max_chunks * g.num_keys * sizeof(uint16_t));
+    l.off_totals = take((size_t)B * g.num_keys * sizeof(int32_t));
+    l.off_slots = take((size_t)B * g.num_keys * g.M * sizeof(float4));
+    l.off_pil_key = take((size_t)B * g.Vmax * sizeof(int32_t));
+    l.off_pil_n = take((size_t)B * g.Vmax * sizeof(int32_t));
+    l.off_pil_coord = take((size_t)B * g.Vmax * sizeof(int32_t));
+    l.off_num_pil = take((size_t)B * sizeof(int32_t));
+    l.off_owner = take((size_t)B * HW * sizeof(int32_t));
+    l.off_cell_desc = take((size_t)B * HW * sizeof(int32_t));
+    l.total_bytes = off;
+    *out = l;
+    return P3P_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_blob(int C, BlobLayout* bl) {
+    if (C < 1 || C > 4096) return fail(P3P_ERR_INVALID_ARGUMENT, "channels %d", C);
+    make_blob_layout(C, bl);
+    return P3P_OK;
+}
+
+static int run_pfn(const PfnArgs& a, int precision, cudaStream_t st) {
+    if (precision == P3P_PRECISION_FP32) return launch_pfn_simt(a, st);
+    if (precision != P3P_PRECISION_TF32 && precision != P3P_PRECISION_BF16)
+        return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+    // The tensor-core kernel covers the shipped encoder configs (M = 64, C <= 384); other shapes of the density
+    // ablation take the exact-fp32 kernel, which is at least as accurate as either tensor-core contract.
+    if (a.g.M == 64 && a.bl.MT <= 3) return launch_pfn_tc(a, precision, st);
+    return launch_pfn_simt(a, st);
+}
+
+}  // namespace p3p
+
+using namespace p3p;
+
+extern "C" {
+
+const char* p3p_last_error(void) { return g_err; }
+int p3p_version(void) { return P3P_VERSION; }
+
+size_t p3p_workspace_bytes(const p3p_grid* grid, int32_t num_tiles, int64_t total_points) {
+    GridDev g;
+    WsLayout l;
+    if (make_grid(grid, &g) != P3P_OK) return 0;
+    if (make_ws_layout(g, num_tiles, total_points, &l) != P3P_OK) return 0;
+    return l.total_bytes;
+}
+
+size_t p3p_pfn_blob_bytes(int32_t channels) {
+    BlobLayout bl;
+    if (check_blob(channels, &bl) != P3P_OK) return 0;
+    return bl.total_bytes;
+}
+
+int p3p_pfn_prepare(const p3p_pfn_params* p, int32_t precision, void* blob, size_t blob_bytes, void* stream) {
+    if (!p || !blob) return fail(P3P_ERR_INVALID_ARGUMENT, "null params or blob");
+    if (!p->linear0_weight || !p->norm0_weight || !p->norm0_bias || !p->norm0_mean || !p->norm0_var ||
+        !p->linear1_weight || !p->norm1_weight || !p->norm1_bias || !p->norm1_mean || !p->norm1_var)
+        return fail(P3P_ERR_INVALID_ARGUMENT, "null weight pointer");
+    if (precision < P3P_PRECISION_FP32 || precision > P3P_PRECISION_BF16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+    BlobLayout bl;
+    int rc = check_blob(p->channels, &bl);
+    if (rc) return rc;
+    if (blob_bytes < bl.total_bytes) return fail(P3P_ERR_WORKSPACE, "blob needs %zu bytes, got %zu", bl.total_bytes, blob_bytes);
+    if (!aligned16(blob)) return fail(P3P_ERR_INVALID_ARGUMENT, "blob must be 16-byte aligned");
+    return launch_pfn_prepare(p, precision, static_cast<char*>(blob), bl, static_cast<cudaStream_t>(stream));
+}
+
+static int common_setup(const float* points, int32_t point_stride, const int64_t* tile_offsets, int32_t B,
+                        int64_t total_points, const p3p_grid* grid, void* workspace, size_t workspace_bytes,
+                        GridDev* g, WsLayout* l, WsPtrs* ws) {
+    if (B < 0) return fail(P3P_ERR_INVALID_ARGUMENT, "num_tiles %d", B);
+    if (B > 0 && !tile_offsets) return fail(P3P_ERR_INVALID_ARGUMENT, "tile_offsets is null");
+    if (total_points > 0 && !points) return fail(P3P_ERR_INVALID_ARGUMENT, "points is null");
+    if (point_stride < 3) return fail(P3P_ERR_INVALID_ARGUMENT, "point_stride %d (< 3)", point_stride);
+    int rc = make_grid(grid, g);
+    if (rc) return rc;
+    rc = make_ws_layout(*g, B, total_points, l);
+    if (rc) return rc;
+    if (!workspace || !aligned16(workspace)) return fail(P3P_ERR_INVALID_ARGUMENT, "workspace null or misaligned");
+    if (workspace_bytes < l->total_bytes) return fail(P3P_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", l->total_bytes, workspace_bytes);
+    *ws = ws_ptrs(workspace, *l);
+    return P3P_OK;
+}
+
+int p3p_voxelize(const float* points, int32_t point_stride, const int64_t* tile_offsets, int32_t num_tiles,
+                 int64_t total_points, const p3p_grid* grid, const p3p_voxel_outputs* out, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    GridDev g;
+    WsLayout l;
+    WsPtrs ws;
+    int rc = common_setup(points, point_stride, tile_offsets, num_tiles, total_points, grid, workspace, workspace_bytes, &g, &l, &ws);
+    if (rc) return rc;
+    if (num_tiles == 0) return P3P_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = launch_voxelize(points, point_stride, tile_offsets, num_tiles, total_points, g, l, ws, out ? out->point_hash : nullptr, st);
+    if (rc) return rc;
+    if (out) return launch_export(g, num_tiles, ws, out, st);
+    return P3P_OK;
+}
+
+static void fill_pfn_args(PfnArgs* a, const GridDev& g, const WsPtrs& ws, const void* blob, const BlobLayout& bl, int B) {
+    memset(a, 0, sizeof(*a));
+    a->g = g;
+    a->ws = ws;
+    a->blob = static_cast<const char*>(blob);
+    a->bl = bl;
+    a->B = B;
+}
+
+int p3p_pillar_features(const p3p_grid* grid, int32_t num_tiles, int64_t total_points, const void* blob, int32_t channels,
+                        int32_t precision, float* features, void* workspace, size_t workspace_bytes, void* stream) {
+    GridDev g;
+    WsLayout l;
+    BlobLayout bl;
+    int rc = make_grid(grid, &g);
+    if (rc) return rc;
+    rc = make_ws_layout(g, num_tiles, total_points, &l);
+    if (rc) return rc;
+    rc = check_blob(channels, &bl);
+    if (rc) return rc;
+    if (!blob || !features || !workspace) return fail(P3P_ERR_INVALID_ARGUMENT, "null blob, features or workspace");
+    if (!aligned16(blob) || !aligned16(features) || !aligned16(workspace)) return fail(P3P_ERR_INVALID_ARGUMENT, "misaligned pointer");
+    if (workspace_bytes < l.total_bytes) return fail(P3P_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", l.total_bytes, workspace_bytes);
+    if (num_tiles == 0) return P3P_OK;
+    PfnArgs a;
+    fill_pfn_args(&a, g, ws_ptrs(workspace, l), blob, bl, num_tiles);
+    a.item_mode = kItemsList;
+    a.items_per_tile = g.Vmax;
+    a.num_items = (int64_t)num_tiles * g.Vmax;
+    a.out = features;
+    a.out_layout = P3P_LAYOUT_NLC;
+    a.out_dtype = P3P_DTYPE_F32;
+    return run_pfn(a, precision, static_cast<cudaStream_t>(stream));
+}
+
+int p3p_encode(const float* points, int32_t point_stride, const int64_t* tile_offsets, int32_t num_tiles,
+               int64_t total_points, const p3p_grid* grid, const void* blob, int32_t channels, int32_t precision, void* out,
+               int32_t out_layout, int32_t out_dtype, int32_t c_total, int32_t c_offset, int32_t lidar_zero,
+               void* workspace, size_t workspace_bytes, void* stream) {
+    GridDev g;
+    WsLayout l;
+    WsPtrs ws;
+    BlobLayout bl;
+    int rc = common_setup(points, point_stride, tile_offsets, num_tiles, total_points, grid, workspace, workspace_bytes, &g, &l, &ws);
+    if (rc) return rc;
+    rc = check_blob(channels, &bl);
+    if (rc) return rc;
+    if (!out || !aligned16(out)) return fail(P3P_ERR_INVALID_ARGUMENT, "out null or misaligned");
+    if (!lidar_zero && (!blob || !aligned16(blob))) return fail(P3P_ERR_INVALID_ARGUMENT, "blob null or misaligned");
+    if (out_layout != P3P_LAYOUT_NCHW && out_layout != P3P_LAYOUT_NLC) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown layout %d", out_layout);
+    if (out_dtype != P3P_DTYPE_F32 && out_dtype != P3P_DTYPE_BF16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown dtype %d", out_dtype);
+    if (out_layout == P3P_LAYOUT_NCHW && (c_offset < 0 || c_offset + channels > c_total))
+        return fail(P3P_ERR_INVALID_ARGUMENT, "channels [%d, %d) outside c_total %d", c_offset, c_offset + channels, c_total);
+    if (num_tiles == 0) return P3P_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PfnArgs a;
+    fill_pfn_args(&a, g, ws, blob, bl, num_tiles);
+    a.item_mode = kItemsCanvas;
+    a.items_per_tile = g.ny * g.nx;
+    a.num_items = (int64_t)num_tiles * a.items_per_tile;
+    a.out = out;
+    a.out_layout = out_layout;
+    a.out_dtype = out_dtype;
+    a.c_total = c_total;
+    a.c_offset = c_offset;
+    if (lidar_zero) return launch_zero_lidar(a, st);  // `x_lidar * 0.0` (early_fusion_vit.py:113-119)
+    rc = launch_voxelize(points, point_stride, tile_offsets, num_tiles, total_points, g, l, ws, nullptr, st);
+    if (rc) return rc;
+    return run_pfn(a, precision, st);
+}
+
+int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, int32_t height, int32_t width,
+                    int32_t patch, const float* weight, const float* bias, int32_t channels, int32_t precision, void* out,
+                    int32_t out_dtype, int32_t c_total, int32_t c_offset, void* stream) {
+    (void)images; (void)num_tiles; (void)in_chans; (void)height; (void)width; (void)patch; (void)weight; (void)bias;
+    (void)channels; (void)precision; (void)out; (void)out_dtype; (void)c_total; (void)c_offset; (void)stream;
+    return fail(P3P_ERR_UNSUPPORTED, "placeholder");
+}
+
+}  // extern "C"

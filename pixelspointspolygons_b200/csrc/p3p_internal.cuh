@@ -1,0 +1,330 @@
+// p3p_internal.cuh -- shared declarations of libp3p.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "p3p.h"
+
+namespace p3p {
+
+// ----------------------------------------------------------------------------------------------
+// error plumbing (capi.cu owns the thread-local message)
+// ----------------------------------------------------------------------------------------------
+int fail(int code, const char* fmt, ...);
+#define P3P_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ::p3p::fail(P3P_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                            \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// grid constants, derived on the host with the same fp32 operations as Open3D's VoxelizeCPU
+//  and passed to every kernel by value
+// ----------------------------------------------------------------------------------------------
+constexpr int kFlagDropOverflow = P3P_GRID_DROP_OVERFLOW;  // DESIGN.md uncertainty ledger U1
+constexpr int kMaxKeys = 6144;        // smem histogram budget of the ranking kernels
+constexpr int kInvalidKey = 0xFFFF;   // uint16 key cache marker
+constexpr int kC0 = 32;               // feat_channels[0] / 2: width of PFN layer 0
+
+struct GridDev {
+    float mn[3], mx[3], inv[3];
+    int ext[3];        // int32(ceil((max - min) * inv))
+    int nv[3];         // int32((max - min) / voxel_size): x/y bound of the pillar filter
+    int stride1, stride2;
+    int num_cells;     // ext0 * ext1 * ext2 (upstream's batch_hash)
+    int num_keys;      // largest reachable hash + 1
+    int M, Vmax, ny, nx;
+    int flags;
+    float vx, vy, x_off, y_off;  // PillarFeatureNet: vx, vy, vx/2 + min_x, vy/2 + min_y
+};
+
+int make_grid(const p3p_grid* g, GridDev* out);
+
+// ----------------------------------------------------------------------------------------------
+// workspace carve-up (all offsets 256-byte aligned)
+// ----------------------------------------------------------------------------------------------
+struct WsLayout {
+    int B;
+    int chunk_points;      // S: points per ranking chunk (multiple of 256)
+    int max_chunks;        // upper bound of the number of chunks over the batch
+    size_t off_chunk_hist; // uint16 [max_chunks][num_keys]
+    size_t off_totals;     // int32  [B][num_keys]   uncapped points per key
+    size_t off_slots;      // float4 [B][num_keys][M] (x, y, z, bits(tile-local index)), rank order
+    size_t off_pil_key;    // int32  [B][Vmax]       key of pillar r (voxel order, after both filters)
+    size_t off_pil_n;      // int32  [B][Vmax]       min(count, M)
+    size_t off_pil_coord;  // int32  [B][Vmax]       cx | cy << 10 | cz << 20
+    size_t off_num_pil;    // int32  [B]
+    size_t off_owner;      // int32  [B][ny*nx]      voxel ordinal owning the canvas cell, -1 = empty
+    size_t off_cell_desc;  // int32  [B][ny*nx]      key | n << 16 of the owning pillar, -1 = empty
+    size_t total_bytes;
+};
+
+int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out);
+
+struct WsPtrs {
+    uint16_t* chunk_hist;
+    int32_t* totals;
+    float4* slots;
+    int32_t* pil_key;
+    int32_t* pil_n;
+    int32_t* pil_coord;
+    int32_t* num_pil;
+    int32_t* owner;
+    int32_t* cell_desc;
+};
+
+inline WsPtrs ws_ptrs(void* base, const WsLayout& l) {
+    char* b = static_cast<char*>(base);
+    WsPtrs p;
+    p.chunk_hist = reinterpret_cast<uint16_t*>(b + l.off_chunk_hist);
+    p.totals = reinterpret_cast<int32_t*>(b + l.off_totals);
+    p.slots = reinterpret_cast<float4*>(b + l.off_slots);
+    p.pil_key = reinterpret_cast<int32_t*>(b + l.off_pil_key);
+    p.pil_n = reinterpret_cast<int32_t*>(b + l.off_pil_n);
+    p.pil_coord = reinterpret_cast<int32_t*>(b + l.off_pil_coord);
+    p.num_pil = reinterpret_cast<int32_t*>(b + l.off_num_pil);
+    p.owner = reinterpret_cast<int32_t*>(b + l.off_owner);
+    p.cell_desc = reinterpret_cast<int32_t*>(b + l.off_cell_desc);
+    return p;
+}
+
+// ----------------------------------------------------------------------------------------------
+// prepared-weights blob (written by pfn_prepare_kernel, read by the PFN kernels)
+// ----------------------------------------------------------------------------------------------
+struct BlobLayout {
+    int C, Cpad, MT;      // channels, padded to 128, number of 128-channel MMA tiles
+    size_t off_header;    // int32[16]: magic, precision, C, Cpad, center_alias
+    size_t off_front;     // float[10][32]: Ux,Uy,Uz, Kcx,Kcy, Wmx,Wmy,Wmz, b0, hpad   (affine form of layer 0)
+    size_t off_w0;        // float[32][8]  a0 * W0           (literal form, fp32 kernel)
+    size_t off_b0;        // float[32]
+    size_t off_w1;        // float[Cpad][64] a1 * W1         (literal form, fp32 kernel)
+    size_t off_b1;        // float[Cpad]
+    size_t off_a1;        // MMA A operand of W1[:, :32] (K-major, swizzled), MT tiles of 128 rows
+    size_t off_a2;        // MMA A operand of W1[:, 32:]
+    size_t total_bytes;
+};
+constexpr int kBlobMagic = 0x50335031;  // "P3P1"
+
+void make_blob_layout(int C, BlobLayout* out);
+
+// item sources of the PFN kernels
+constexpr int kItemsCanvas = 0;  // item = b * (ny*nx) + cell, resolved through the owner table
+constexpr int kItemsList = 1;    // item = b * Vmax + r, r < num_pil[b]
+
+struct PfnArgs {
+    GridDev g;
+    WsPtrs ws;
+    const char* blob;
+    BlobLayout bl;
+    int B;
+    int item_mode;
+    int64_t num_items;
+    int items_per_tile;
+    // output addressing: NLC / list: out[item * C + c]; NCHW: out[((b * c_total + c_offset + c) * HW) + cell]
+    void* out;
+    int out_layout;  // P3P_LAYOUT_*
+    int out_dtype;   // P3P_DTYPE_*
+    int c_total, c_offset;
+};
+
+// launchers (host) ---------------------------------------------------------------------------------
+int launch_voxelize(const float* pts, int stride, const int64_t* offsets, int B, int64_t total, const GridDev& g,
+                    const WsLayout& l, const WsPtrs& ws, int32_t* point_hash, cudaStream_t st);
+int launch_export(const GridDev& g, int B, const WsPtrs& ws, const p3p_voxel_outputs* out, cudaStream_t st);
+int launch_pfn_prepare(const p3p_pfn_params* p, int precision, char* blob, const BlobLayout& bl, cudaStream_t st);
+int launch_pfn_simt(const PfnArgs& a, cudaStream_t st);
+int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st);
+int launch_zero_lidar(const PfnArgs& a, cudaStream_t st);
+int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, int P, const float* weight,
+                       const float* bias, int C, int precision, void* out, int out_dtype, int c_total, int c_offset,
+                       cudaStream_t st);
+int device_sm_count();
+
+// ----------------------------------------------------------------------------------------------
+// device helpers
+// ----------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// cell hash of one point, or -1 (Open3D VoxelizeCPU HashFn; fp32 subtract then multiply, truncation)
+__device__ __forceinline__ int point_key(const GridDev& g, float x, float y, float z) {
+    const bool valid = (x >= g.mn[0]) && (x <= g.mx[0]) && (y >= g.mn[1]) && (y <= g.mx[1]) && (z >= g.mn[2]) &&
+                       (z <= g.mx[2]);
+    if (!valid) return -1;
+    const int cx = __float2int_rz(__fmul_rn(__fsub_rn(x, g.mn[0]), g.inv[0]));
+    const int cy = __float2int_rz(__fmul_rn(__fsub_rn(y, g.mn[1]), g.inv[1]));
+    const int cz = __float2int_rz(__fmul_rn(__fsub_rn(z, g.mn[2]), g.inv[2]));
+    const int h = cx + cy * g.stride1 + cz * g.stride2;
+    if ((g.flags & kFlagDropOverflow) && h >= g.num_cells) return -1;
+    return h;
+}
+
+__device__ __forceinline__ void point_cell(const GridDev& g, float x, float y, float z, int& cx, int& cy, int& cz) {
+    cx = __float2int_rz(__fmul_rn(__fsub_rn(x, g.mn[0]), g.inv[0]));
+    cy = __float2int_rz(__fmul_rn(__fsub_rn(y, g.mn[1]), g.inv[1]));
+    cz = __float2int_rz(__fmul_rn(__fsub_rn(z, g.mn[2]), g.inv[2]));
+}
+
+// One pillar as seen by the PFN kernels.
+struct Item {
+    int valid;            // 0: empty canvas cell / padding row of the list
+    int b;                // tile
+    int n;                // min(count, M)
+    int key;              // slot row of the pillar
+    float ctr_x, ctr_y;   // pillar centre: cx * vx + x_off, cy * vy + y_off
+    int cell;             // canvas cell (cy * nx + cx)
+};
+
+__device__ __forceinline__ const float4* item_slots(const PfnArgs& a, const Item& it) {
+    return a.ws.slots + ((int64_t)it.b * a.g.num_keys + it.key) * a.g.M;
+}
+
+// One dependent-load level: canvas items read cell_desc, list items read the pillar table.
+__device__ __forceinline__ Item fetch_item(const PfnArgs& a, int64_t item) {
+    Item it;
+    it.valid = 0; it.n = 0; it.key = 0; it.ctr_x = 0.f; it.ctr_y = 0.f; it.cell = 0; it.b = 0;
+    if (item >= a.num_items) return it;
+    const int b = (int)(item / a.items_per_tile);
+    const int r = (int)(item - (int64_t)b * a.items_per_tile);
+    it.b = b;
+    int cx, cy;
+    if (a.item_mode == kItemsCanvas) {
+        const int d = __ldg(a.ws.cell_desc + item);
+        it.cell = r;
+        if (d < 0) return it;
+        it.key = d & 0xFFFF;
+        it.n = d >> 16;
+        cy = r / a.g.nx;
+        cx = r - cy * a.g.nx;
+    } else {
+        if (r >= a.ws.num_pil[b]) return it;
+        const int64_t pi = (int64_t)b * a.g.Vmax + r;
+        it.key = a.ws.pil_key[pi];
+        it.n = a.ws.pil_n[pi];
+        const int pc = a.ws.pil_coord[pi];
+        cx = pc & 1023;
+        cy = (pc >> 10) & 1023;
+        it.cell = cy * a.g.nx + cx;
+    }
+    it.valid = 1;
+    it.ctr_x = __fmaf_rn((float)cx, a.g.vx, a.g.x_off);
+    it.ctr_y = __fmaf_rn((float)cy, a.g.vy, a.g.y_off);
+    return it;
+}
+
+// ---- mbarrier -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{.reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0];}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- tcgen05 --------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrive on an mbarrier when all tcgen05 ops previously issued by this thread have completed
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    if constexpr (kTf32) {
+        asm volatile(
+            "{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    } else {
+        asm volatile(
+            "{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    }
+}
+// K-major smem operand descriptor (cute::UMMA::SmemDescriptor, version 1): 8-row groups `sbo` bytes apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t hi = (sbo_bytes >> 4) | (1u << 14) | (layout_type << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// cute::UMMA::InstrDescriptor: dense, fp32 accumulate, both operands K-major
+__device__ __forceinline__ uint32_t make_idesc(bool tf32, int m, int n) {
+    const uint32_t fmt = tf32 ? 2u : 1u;  // F16F32Format: TF32 = 2, BF16 = 1
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// tcgen05.ld + tcgen05.wait::ld in ONE asm statement: the destination registers are only defined once the
+// wait has retired, so no consumer can be scheduled between the load and the wait.
+__device__ __forceinline__ void tmem_ld64_wait(uint32_t taddr, float (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15]),"=f"(v[16]),"=f"(v[17]),"=f"(v[18]),"=f"(v[19]),"=f"(v[20]),"=f"(v[21]),"=f"(v[22]),"=f"(v[23]),"=f"(v[24]),"=f"(v[25]),"=f"(v[26]),"=f"(v[27]),"=f"(v[28]),"=f"(v[29]),"=f"(v[30]),"=f"(v[31]),"=f"(v[32]),"=f"(v[33]),"=f"(v[34]),"=f"(v[35]),"=f"(v[36]),"=f"(v[37]),"=f"(v[38]),"=f"(v[39]),"=f"(v[40]),"=f"(v[41]),"=f"(v[42]),"=f"(v[43]),"=f"(v[44]),"=f"(v[45]),"=f"(v[46]),"=f"(v[47]),"=f"(v[48]),"=f"(v[49]),"=f"(v[50]),"=f"(v[51]),"=f"(v[52]),"=f"(v[53]),"=f"(v[54]),"=f"(v[55]),"=f"(v[56]),"=f"(v[57]),"=f"(v[58]),"=f"(v[59]),"=f"(v[60]),"=f"(v[61]),"=f"(v[62]),"=f"(v[63])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld2_wait(uint32_t taddr, float& a, float& b) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=f"(a), "=f"(b)
+        : "r"(taddr)
+        : "memory");
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float warp_max_f32(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace p3p

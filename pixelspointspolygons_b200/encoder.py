@@ -1,0 +1,288 @@
+"""Drop-in replacement of the reference's LiDAR encoder module.
+
+`PointPillarsEncoder` mirrors R:pixelspointspolygons/models/pointpillars/pointpillars_o3d.py:11-107:
+same constructor `(cfg, voxel_encoder, scatter, local_rank=0)`, same cfg fields (:39-47), same
+`forward(x_lidar, return_flattened=True)` (:85-107), same state_dict keys as the Open3D-ML modules it
+subclasses there (`voxel_encoder.pfn_layers.{0,1}.{linear.weight, norm.*}`), so published
+checkpoints load with `strict=True`.  Inference runs entirely in libp3p.so (hand-written sm_100a kernels behind
+the C ABI of include/p3p.h); there is no CPU or eager fallback for it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import P3P_DTYPE_BF16, P3P_DTYPE_F32, P3P_LAYOUT_NCHW, P3P_LAYOUT_NLC, P3P_PRECISION
+
+
+def _get(node, key, default=None):
+    if node is None:
+        return default
+    if isinstance(node, dict):
+        return node.get(key, default)
+    try:
+        return getattr(node, key)
+    except Exception:
+        try:
+            return node[key]
+        except Exception:
+            return default
+
+
+class PFNLayer(nn.Module):
+    """Parameter holder with the upstream names; its dense `forward` is only used by the training path."""
+
+    def __init__(self, in_channels: int, out_channels: int, last_layer: bool = False):
+        super().__init__()
+        self.last_vfe = last_layer
+        self.units = out_channels if last_layer else out_channels // 2
+        self.norm = nn.BatchNorm1d(self.units, eps=1e-3, momentum=0.01)
+        self.linear = nn.Linear(in_channels, self.units, bias=False)
+
+    def forward(self, inputs):
+        x = self.linear(inputs)
+        x = self.norm(x.permute(0, 2, 1).contiguous()).permute(0, 2, 1).contiguous()
+        x = F.relu(x)
+        x_max = torch.max(x, dim=1, keepdim=True)[0]
+        if self.last_vfe:
+            return x_max
+        return torch.cat([x, x_max.expand(-1, inputs.shape[1], -1)], dim=2)
+
+
+class PillarFeatureNet(nn.Module):
+    def __init__(self, in_channels=3, feat_channels=(64, 384), voxel_size=(8, 8, 100), point_cloud_range=(0, 0, 0, 224, 224, 100)):
+        super().__init__()
+        chans = [in_channels + 5] + list(feat_channels)
+        self.pfn_layers = nn.ModuleList(
+            [PFNLayer(chans[i], chans[i + 1], last_layer=(i == len(chans) - 2)) for i in range(len(chans) - 1)])
+        self.vx, self.vy = float(voxel_size[0]), float(voxel_size[1])
+        self.x_offset = self.vx / 2 + point_cloud_range[0]
+        self.y_offset = self.vy / 2 + point_cloud_range[1]
+
+    def forward(self, features, num_points, coors, center_alias=True):
+        """Dense autograd formulation (training only; BN batch statistics over every slot, padded ones included)."""
+        mean = features[:, :, :3].sum(dim=1, keepdim=True) / num_points.type_as(features).view(-1, 1, 1)
+        f_cluster = features[:, :, :3] - mean
+        cx = coors[:, 3].to(features.dtype).unsqueeze(1) * self.vx + self.x_offset
+        cy = coors[:, 2].to(features.dtype).unsqueeze(1) * self.vy + self.y_offset
+        f_center = torch.stack([features[:, :, 0] - cx, features[:, :, 1] - cy], dim=-1)
+        head = torch.cat([f_center, features[:, :, 2:3]], dim=-1) if center_alias else features[:, :, :3]
+        x = torch.cat([head, f_cluster, f_center], dim=-1)
+        mask = (torch.arange(x.shape[1], device=x.device).view(1, -1) < num_points.view(-1, 1)).unsqueeze(-1)
+        x = x * mask.type_as(x)
+        for pfn in self.pfn_layers:
+            x = pfn(x)
+        return x.squeeze(1)
+
+
+class PointPillarsEncoder(nn.Module):
+    def __init__(self, cfg, voxel_encoder: dict, scatter: dict, local_rank: int = 0):
+        super().__init__()
+        self.cfg = cfg
+        verbosity = getattr(logging, str(_get(_get(cfg, "run_type"), "logging", "INFO")).upper(), logging.INFO)
+        self.logger = logging.getLogger(f"{self.__class__.__name__}[{local_rank}]")
+        self.logger.setLevel(verbosity)
+        enc = cfg.experiment.encoder
+        vs = enc.in_voxel_size
+        voxel_size = [float(v) for v in (vs.values() if hasattr(vs, "values") else vs)]
+        if len(voxel_size) != 3:
+            raise ValueError("cfg.experiment.encoder.in_voxel_size must have x, y, z")
+        self.voxel_size = voxel_size
+        self.point_cloud_range = [0.0, 0.0, 0.0, float(enc.in_width), float(enc.in_height), float(voxel_size[2])]
+        self.max_num_points = int(enc.max_num_points_per_voxel)
+        self.max_voxels = [int(enc.max_num_voxels.train), int(enc.max_num_voxels.test)]
+        feat_channels = list(voxel_encoder["feat_channels"])
+        if len(feat_channels) != 2 or feat_channels[0] != 64:
+            raise NotImplementedError("PillarFeatureNet feat_channels must be [64, C] (pointpillars_vit.py:57-58)")
+        if int(voxel_encoder.get("in_channels", 3)) != 3:
+            raise NotImplementedError("in_channels must be 3 (xyz), as in the reference encoders")
+        self.channels = int(feat_channels[1])
+        if int(scatter["in_channels"]) != self.channels:
+            raise ValueError("scatter.in_channels must equal feat_channels[-1]")
+        self.ny, self.nx = int(scatter["output_shape"][0]), int(scatter["output_shape"][1])
+        self.voxel_encoder = PillarFeatureNet(3, feat_channels, voxel_size, self.point_cloud_range)
+        self.center_alias = bool(_get(enc, "p3p_center_alias", True))          # DESIGN.md ledger U2
+        self.drop_overflow = bool(_get(enc, "p3p_drop_overflow", False))       # DESIGN.md ledger U1
+        self.precision = str(_get(enc, "p3p_precision", None) or os.environ.get("P3P_PRECISION", "tf32")).lower()
+        if self.precision not in P3P_PRECISION:
+            raise ValueError(f"p3p_precision must be one of {sorted(P3P_PRECISION)}")
+        self.out_dtype = torch.float32
+        self._ws: Optional[torch.Tensor] = None
+        self._blobs = {}
+        self._dense_offsets = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _grid(self, training: Optional[bool] = None) -> _lib.Grid:
+        training = self.training if training is None else training
+        mv = self.max_voxels[0] if training else self.max_voxels[1]
+        return _lib.make_grid(self.point_cloud_range[:3], self.point_cloud_range[3:], self.voxel_size, self.max_num_points,
+                              mv, self.ny, self.nx, _lib.P3P_GRID_DROP_OVERFLOW if self.drop_overflow else 0)
+
+    def _pack(self, x_lidar) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        """-> (values (sumN, stride) fp32 contiguous, offsets (B+1) int64 on the same device, B)."""
+        if isinstance(x_lidar, (list, tuple)):
+            lens = [int(t.shape[0]) for t in x_lidar]
+            values = torch.cat([t.reshape(-1, t.shape[-1]) for t in x_lidar], 0) if lens else torch.zeros(0, 3)
+            offs = torch.tensor([0] + list(torch.tensor(lens).cumsum(0).tolist()) if lens else [0], dtype=torch.int64)
+            offsets = offs.to(values.device, non_blocking=True)
+            B = len(lens)
+        elif x_lidar.is_nested:
+            values, offsets, B = x_lidar.values(), x_lidar.offsets(), x_lidar.shape[0]
+            if offsets.dtype != torch.int64:
+                offsets = offsets.to(torch.int64)
+        else:
+            if x_lidar.dim() != 3:
+                raise ValueError("x_lidar must be a jagged NestedTensor (B, j, 3) or a dense (B, N, 3) tensor")
+            B, N = x_lidar.shape[0], x_lidar.shape[1]
+            values = x_lidar.reshape(B * N, x_lidar.shape[2])
+            key = (B, N, values.device)
+            offsets = self._dense_offsets.get(key)
+            if offsets is None:
+                offsets = torch.arange(B + 1, dtype=torch.int64, device=values.device) * N
+                self._dense_offsets = {key: offsets}
+        if values.dtype != torch.float32:
+            raise TypeError(f"x_lidar must be float32, got {values.dtype}")
+        if not values.is_cuda:
+            raise RuntimeError("PointPillarsEncoder runs on CUDA only (sm_100a); x_lidar is on " + str(values.device))
+        if values.dim() != 2 or values.shape[1] < 3:
+            raise ValueError("points need at least 3 channels (x, y, z)")
+        return values.contiguous(), offsets.contiguous(), int(B)
+
+    def _workspace(self, grid, B, total, device) -> torch.Tensor:
+        need = _lib.lib().p3p_workspace_bytes(C.byref(grid), B, total)
+        if need == 0 and B > 0:
+            _lib.check(-1, "p3p_workspace_bytes")
+        if self._ws is None or self._ws.device != device or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 1), dtype=torch.uint8, device=device)
+        return self._ws
+
+    def _blob(self, device, precision: str) -> torch.Tensor:
+        l0, l1 = self.voxel_encoder.pfn_layers[0], self.voxel_encoder.pfn_layers[1]
+        tensors = [l0.linear.weight, l0.norm.weight, l0.norm.bias, l0.norm.running_mean, l0.norm.running_var,
+                   l1.linear.weight, l1.norm.weight, l1.norm.bias, l1.norm.running_mean, l1.norm.running_var]
+        stamp = tuple((t._version, t.data_ptr()) for t in tensors) + (self.center_alias,)
+        hit = self._blobs.get((precision, device))
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        for t in tensors:
+            if t.device != device or t.dtype != torch.float32:
+                raise RuntimeError("PFN parameters must be float32 on the device of x_lidar")
+        keep = [t.detach().contiguous() for t in tensors]
+        p = _lib.PfnParams()
+        for name, t in zip(("linear0_weight", "norm0_weight", "norm0_bias", "norm0_mean", "norm0_var",
+                            "linear1_weight", "norm1_weight", "norm1_bias", "norm1_mean", "norm1_var"), keep):
+            setattr(p, name, t.data_ptr())
+        p.eps, p.channels, p.center_alias = float(l0.norm.eps), self.channels, int(self.center_alias)
+        nbytes = _lib.lib().p3p_pfn_blob_bytes(self.channels)
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.check(_lib.lib().p3p_pfn_prepare(C.byref(p), P3P_PRECISION[precision], blob.data_ptr(), nbytes,
+                                              torch.cuda.current_stream(device).cuda_stream), "p3p_pfn_prepare")
+        self._blobs[(precision, device)] = (stamp, blob)
+        return blob
+
+    # ------------------------------------------------------------------ fused inference path
+    def encode_into(self, x_lidar, out: torch.Tensor, layout: int, c_total: int = 0, c_offset: int = 0,
+                    lidar_zero: bool = False, precision: Optional[str] = None) -> torch.Tensor:
+        """voxelize -> PFN -> scatter, written into `out` (NLC (B, ny*nx, C) or NCHW channels [c_offset, c_offset+C))."""
+        values, offsets, B = self._pack(x_lidar)
+        precision = precision or self.precision
+        device = values.device
+        grid = self._grid()
+        total = values.shape[0]
+        with torch.cuda.device(device):
+            ws = self._workspace(grid, B, total, device)
+            blob = self._blob(device, precision)
+            dt = P3P_DTYPE_F32 if out.dtype == torch.float32 else P3P_DTYPE_BF16
+            rc = _lib.lib().p3p_encode(values.data_ptr(), values.shape[1], offsets.data_ptr(), B, total, C.byref(grid),
+                                       blob.data_ptr(), self.channels, P3P_PRECISION[precision], out.data_ptr(), layout, dt,
+                                       c_total, c_offset, int(lidar_zero), ws.data_ptr(), ws.numel(),
+                                       torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "p3p_encode")
+        return out
+
+    def forward(self, x_lidar, return_flattened: bool = True):
+        if self.training:
+            return self._forward_dense(x_lidar, return_flattened)
+        values, offsets, B = self._pack(x_lidar)
+        hw = self.ny * self.nx
+        if return_flattened:
+            out = torch.empty(B, hw, self.channels, dtype=self.out_dtype, device=values.device)
+            return self.encode_into(x_lidar, out, P3P_LAYOUT_NLC)
+        out = torch.empty(B, self.channels, self.ny, self.nx, dtype=self.out_dtype, device=values.device)
+        return self.encode_into(x_lidar, out, P3P_LAYOUT_NCHW, c_total=self.channels, c_offset=0)
+
+    # ------------------------------------------------------------------ parity / training surface
+    @torch.no_grad()
+    def voxelize_raw(self, x_lidar, want_points: bool = True):
+        """Integer outputs of the voxelizer, padded per tile to max_voxels rows (see p3p_voxel_outputs)."""
+        values, offsets, B = self._pack(x_lidar)
+        device, grid, total = values.device, self._grid(), values.shape[0]
+        M, V, hw = self.max_num_points, grid.max_voxels, self.ny * self.nx
+        i32 = dict(dtype=torch.int32, device=device)
+        res = dict(
+            point_hash=torch.empty(max(total, 1), **i32), num_pillars=torch.zeros(B, **i32),
+            pillar_coords=torch.zeros(B, V, 4, **i32), pillar_num_points=torch.zeros(B, V, **i32),
+            pillar_point_idx=torch.full((B, V, M), -1, **i32), cell_owner=torch.full((B, hw), -1, **i32),
+            pillar_points=torch.zeros(B, V, M, 3, dtype=torch.float32, device=device) if want_points else None)
+        o = _lib.VoxelOutputs()
+        for k, t in res.items():
+            setattr(o, k, t.data_ptr() if t is not None else None)
+        with torch.cuda.device(device):
+            ws = self._workspace(grid, B, total, device)
+            rc = _lib.lib().p3p_voxelize(values.data_ptr(), values.shape[1], offsets.data_ptr(), B, total, C.byref(grid),
+                                         C.byref(o), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "p3p_voxelize")
+        res["point_hash"] = res["point_hash"][:total]
+        res["_ctx"] = (grid, B, total, device)
+        return res
+
+    @torch.no_grad()
+    def voxelize(self, x_lidar):
+        """(voxels (V, M, 3), num_points (V,), coors (V, 4) [b, z, y, x]) -- Open3D-ML PointPillars.voxelize."""
+        r = self.voxelize_raw(x_lidar)
+        V = r["pillar_coords"].shape[1]
+        mask = torch.arange(V, device=r["num_pillars"].device).view(1, -1) < r["num_pillars"].view(-1, 1)
+        return r["pillar_points"][mask], r["pillar_num_points"][mask].to(torch.int64), r["pillar_coords"][mask]
+
+    @torch.no_grad()
+    def pillar_features(self, x_lidar, precision: Optional[str] = None):
+        """((V, C) pillar features in voxel order, coors (V, 4)) -- voxelize + PillarFeatureNet, before the scatter."""
+        r = self.voxelize_raw(x_lidar, want_points=False)
+        grid, B, total, device = r["_ctx"]
+        precision = precision or self.precision
+        V = grid.max_voxels
+        feats = torch.zeros(B, V, self.channels, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            blob = self._blob(device, precision)
+            rc = _lib.lib().p3p_pillar_features(C.byref(grid), B, total, blob.data_ptr(), self.channels, P3P_PRECISION[precision],
+                                                feats.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                                torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "p3p_pillar_features")
+        mask = torch.arange(V, device=device).view(1, -1) < r["num_pillars"].view(-1, 1)
+        return feats[mask], r["pillar_coords"][mask]
+
+    def _forward_dense(self, x_lidar, return_flattened: bool):
+        """Training step: CUDA voxelizer (no grad, like the reference's @torch.no_grad voxelize) + dense autograd PFN
+        with BatchNorm batch statistics / SyncBatchNorm, then the scatter.  Not the measured path."""
+        voxels, num_points, coors = self.voxelize(x_lidar)
+        B = len(x_lidar) if isinstance(x_lidar, (list, tuple)) else x_lidar.shape[0]
+        feats = self.voxel_encoder(voxels, num_points, coors, self.center_alias)
+        hw = self.ny * self.nx
+        canvas = feats.new_zeros(B * hw, self.channels)
+        flat = coors[:, 0].long() * hw + coors[:, 2].long() * self.nx + coors[:, 3].long()
+        # duplicates (z-layer-1 pillars): the last pillar in voxel order owns the cell
+        order = torch.arange(flat.numel(), device=flat.device)
+        winner = torch.full((B * hw,), -1, dtype=torch.long, device=flat.device).scatter_reduce(0, flat, order, "amax")
+        sel = winner >= 0
+        canvas[sel] = feats[winner[sel]]
+        x = canvas.view(B, hw, self.channels)
+        if return_flattened:
+            return x
+        return x.transpose(1, 2).reshape(B, self.channels, self.ny, self.nx)
