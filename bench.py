@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the LiDAR pillar-encode (+ early-fusion) hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload lidar|fusion]
+
+A step is one pass of the hot path over one batch of synthetic tiles (BASELINE.json configs[1]: Pix2Poly
+LiDAR-only, 224 px tiles, 100k points per tile, batch 16 per GPU).  Under torchrun (N > 1) every rank encodes its
+own batch (tiles are independent units: no collective on the data path, weak scaling), the step time is the MAX
+over ranks and `value` is the whole-job tiles/s.  One JSON line is printed by rank 0.
+
+  value         device-timed (CUDA events), inputs resident in HBM, rotating over input/output sets larger than L2
+  e2e           same metric through the public module API with HOST pinned inputs: H2D copy of the step's points +
+                offsets and a D2H read of the step's result checksum inside the timed region
+  roofline      the dominant kernel (PFN tensor-core kernel): algorithmic FLOPs / its CUDA-event duration
+  hbm_roofline  whole-path algorithmic bytes * tiles/s over the measured copy bandwidth (BASELINE's "% HBM roofline")
+  cpu_baseline  the oracle (CPU restatement of the reference path) timed on the host cores on a bounded sample
+
+`--impl reference` times the reference's CPU implementation of the path: the oracle port (open3d==0.19.0, which
+holds the reference's arithmetic, is not installable offline -- DESIGN.md), all host threads, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "pillar_encode_tiles_per_sec"
+UNIT = "tiles/s"
+HW = 28 * 28
+C_FEAT = 384
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lidar", choices=["lidar", "fusion"])
+    ap.add_argument("--batch", type=int, default=16, help="tiles per GPU per step")
+    ap.add_argument("--points", type=int, default=100_000, help="points per tile")
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--max-points-per-voxel", type=int, default=64)
+    ap.add_argument("--sets", type=int, default=8, help="rotating input/output sets (must exceed L2 in total)")
+    ap.add_argument("--no-graph", action="store_true", help="launch through the C ABI every step instead of CUDA graphs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def algorithmic_bytes_per_tile(n_points, workload):
+    """LiDAR-only 12 N + 4 C ny nx; early fusion 12 N + 4*3*224*224 + 4*768*784 (fp32 I/O)."""
+    if workload == "fusion":
+        return 12 * n_points + 4 * 3 * 224 * 224 + 4 * 768 * HW
+    return 12 * n_points + 4 * C_FEAT * HW
+
+
+def algorithmic_flops(tiles, M):
+    """SURVEY 8(d) minimal exact form: 2*8*32*(K + [Pp>0]) + 2*32*384*(K + Pp) + 2*32*384*P over the batch."""
+    K = P = Pp = 0
+    for t in tiles:
+        cx = np.minimum((t[:, 0] * np.float32(0.125)).astype(np.int64), 28)
+        cy = np.minimum((t[:, 1] * np.float32(0.125)).astype(np.int64), 28)
+        ok = (cx < 28) & (cy < 28) & (t[:, 2] < 100.0)
+        cnt = np.bincount((cy * 28 + cx)[ok], minlength=HW)
+        kept = np.minimum(cnt, M)
+        K += int(kept.sum())
+        P += int((cnt > 0).sum())
+        Pp += int(((cnt > 0) & (cnt < M)).sum())
+    return 2 * 8 * 32 * (K + (1 if Pp else 0)) + 2 * 32 * C_FEAT * (K + Pp) + 2 * 32 * C_FEAT * P, K, P
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_modules(M):
+    from oracle import pillars_oracle as po
+
+    grid = po.GridSpec(max_num_points=M)
+    enc = po.OraclePointPillarsEncoder(grid).eval()
+    sd, sdi = po.synth_weights(0)
+    enc.load_state_dict(sd)
+    pe = po.OraclePatchEmbed().eval()
+    pe.load_state_dict(sdi)
+    return po, enc, pe
+
+
+def cpu_step(po, enc, pe, tiles, images, workload):
+    with torch.no_grad():
+        if workload == "fusion":
+            return po.early_fusion_front(pe, enc, images, tiles)
+        return enc(tiles, return_flattened=True)
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the CPU restatement of the reference path on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import pillars_oracle as po_mod  # noqa: F401
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    po, enc, pe = cpu_oracle_modules(args.max_points_per_voxel)
+    tiles_all = [po.synth_tile(args.points, 1000 + i, clustered=(i % 2 == 1)) for i in range(min(args.batch, 4))]
+    img_all = torch.rand(len(tiles_all), 3, 224, 224)
+    t0 = time.perf_counter()
+    cpu_step(po, enc, pe, tiles_all[:1], img_all[:1], args.workload)
+    t_tile = time.perf_counter() - t0
+    budget = 150.0
+    n = int(max(1, min(len(tiles_all), budget / max(t_tile, 1e-3) / max(args.steps + args.warmup, 1))))
+    tiles, images = tiles_all[:n], img_all[:n]
+    for _ in range(args.warmup):
+        cpu_step(po, enc, pe, tiles, images, args.workload)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(po, enc, pe, tiles, images, args.workload)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{n} of {args.batch} tiles per step ({args.points} pts/tile), {args.steps} steps, tiles/s scales per tile"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mpoints_per_s": value * args.points / 1e6,
+        "note": "reference CPU path, restated (open3d 0.19.0 not installable offline); runs on rank 0 only",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    name = ("Pix2Poly LiDAR-only (PointPillars front end of lidar_pp_vit)" if args.workload == "lidar"
+            else "Pix2Poly early fusion (image patch embed + LiDAR pillars -> concat)")
+    return {"workload": f"{name}, synthetic 224px tiles, {args.points} pts/tile, batch {args.batch} per GPU",
+            "tiles_per_gpu": args.batch, "points_per_tile": args.points, "max_points_per_voxel": args.max_points_per_voxel,
+            "precision": args.precision,
+            "l2": f"rotating {args.sets} input+output sets per GPU (> 126 MB L2 in total)",
+            "parallelism": f"tiles sharded batch-wise over {args.gpus} GPU(s), no collective"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    import torch.distributed as dist
+
+    from pixelspointspolygons_b200 import PointPillarsEncoder, _lib, default_cfg
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from oracle import pillars_oracle as po  # synthetic inputs + weights only (the checker's generators)
+
+    B, N, M = args.batch, args.points, args.max_points_per_voxel
+    cfg = default_cfg(device=str(dev), max_num_points_per_voxel=M, p3p_precision=args.precision)
+    enc = PointPillarsEncoder(cfg, voxel_encoder={"in_channels": 3, "feat_channels": [64, C_FEAT]},
+                              scatter={"in_channels": C_FEAT, "output_shape": [28, 28]}).to(dev).eval()
+    sd, sdi = po.synth_weights(0)
+    enc.load_state_dict(sd)
+    fusion = None
+    if args.workload == "fusion":
+        from pixelspointspolygons_b200.fusion import EarlyFusionFrontEnd
+
+        fusion = EarlyFusionFrontEnd(cfg).to(dev).eval()
+        fusion.lidar_embed.load_state_dict(sd)
+        fusion.image_embed.load_state_dict(sdi)
+
+    # ---- synthetic inputs: `sets` distinct batches per GPU, resident in HBM ------------------------------------
+    sets = max(2, args.sets)
+    host_tiles = []
+    for s in range(sets):
+        host_tiles.append([po.synth_tile(N, 1000 * (1 + rank) + 16 * s + i, clustered=(i % 2 == 1)) for i in range(B)])
+    pinned_vals = [torch.from_numpy(np.concatenate(t)).pin_memory() for t in host_tiles]
+    offs = torch.arange(B + 1, dtype=torch.int64) * N
+    pinned_offs = offs.clone().pin_memory()
+    dev_vals = [v.to(dev) for v in pinned_vals]
+    dev_offs = offs.to(dev)
+    dev_x = [torch.nested.nested_tensor_from_jagged(v, dev_offs) for v in dev_vals]
+    if fusion is not None:
+        pinned_img = [torch.rand(B, 3, 224, 224).pin_memory() for _ in range(sets)]
+        dev_img = [p.to(dev) for p in pinned_img]
+        outs = [torch.empty(B, 2 * C_FEAT, 28, 28, device=dev) for _ in range(sets)]
+    else:
+        outs = [torch.empty(B, HW, C_FEAT, device=dev) for _ in range(sets)]
+    flops, kept, pillars = algorithmic_flops(host_tiles[0], M)
+
+    def step(i):
+        s = i % sets
+        if fusion is not None:
+            fusion.forward_into(dev_img[s], dev_x[s], outs[s])
+        else:
+            enc.encode_into(dev_x[s], outs[s], _lib.P3P_LAYOUT_NLC)
+
+    stream = torch.cuda.current_stream(dev)
+    for i in range(sets):
+        step(i)
+    torch.cuda.synchronize()
+    launches_per_step = 2 if fusion is None else 3  # voxelize + PFN (+ patch embed); the counter memset is not a kernel
+    graphs = None
+    if not args.no_graph:
+        # capture one CUDA graph per rotating set: the steady-state serving loop replays them
+        side = torch.cuda.Stream(dev)
+        graphs = []
+        with torch.cuda.stream(side):
+            for s in range(sets):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    step(s)
+                graphs.append(g)
+        torch.cuda.synchronize()
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % sets].replay()
+        else:
+            step(i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: device time of K steps, max over ranks ---------------------------------------------------
+    for i in range(args.warmup):
+        run_step(i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run_step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    tiles_total = B * world * args.steps
+    value = tiles_total / (ms_total * 1e-3)
+
+    # ---- end to end through the module API with host buffers ------------------------------------------------------
+    e2e_steps = max(3, min(args.steps, 50))
+    d_vals = torch.empty_like(dev_vals[0])
+    d_offs = torch.empty_like(dev_offs)
+    h_res = torch.empty(B, dtype=torch.float32).pin_memory()
+    if fusion is not None:
+        d_img = torch.empty_like(dev_img[0])
+
+    def e2e_step(i):
+        s = i % sets
+        d_vals.copy_(pinned_vals[s], non_blocking=True)
+        d_offs.copy_(pinned_offs, non_blocking=True)
+        x = torch.nested.nested_tensor_from_jagged(d_vals, d_offs)
+        if fusion is not None:
+            d_img.copy_(pinned_img[s], non_blocking=True)
+            y = fusion(d_img, x)
+        else:
+            y = enc(x, return_flattened=True)
+        h_res.copy_(y.reshape(B, -1).sum(dim=1), non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * e2e_steps / (float(ms2.item()) * 1e-3)
+    h2d = pinned_vals[0].numel() * 4 + pinned_offs.numel() * 8 + (pinned_img[0].numel() * 4 if fusion is not None else 0)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_res.numel() * 4),
+           "steps": e2e_steps, "result_read": "per-tile checksum of the encoder output"}
+
+    # ---- per-kernel durations (CUDA events recorded inside p3p_encode on the launching stream) ----------------
+    prof_steps = max(3, min(args.steps, 100))
+    l = _lib.lib()
+    _lib.check(l.p3p_profile_begin(prof_steps), "p3p_profile_begin")
+    for i in range(prof_steps):
+        step(i)
+    arr = [(C.c_float * prof_steps)() for _ in range(2)]
+    cnt = C.c_int32(0)
+    _lib.check(l.p3p_profile_end(arr[0], arr[1], prof_steps, C.byref(cnt)), "p3p_profile_end")
+    stage_ms = {n: (statistics.mean(list(a)[:cnt.value]) if cnt.value else None) for n, a in zip(("voxelize", "pfn"), arr)}
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    which = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+    tensor_peak = bf16_peak if args.precision == "bf16" else bf16_peak / 2.0  # tf32 dense = half the bf16 rate
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "pfn_traffic.json"))).get(args.precision)
+    except Exception:
+        pass
+    pfn_s = (stage_ms["pfn"] or 0.0) * 1e-3
+    achieved_tf = flops / pfn_s / 1e12 if pfn_s > 0 else None
+    roofline = {"kernel": "pfn_tc_kernel" if (args.precision != "fp32" and M == 64) else "pfn_simt_kernel",
+                "bound": "tensor", "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": (achieved_tf / tensor_peak) if achieved_tf else None, "traffic": traffic,
+                "peak_source": which + ("; tf32 peak taken as bf16/2" if args.precision != "bf16" else ""),
+                "flops_per_launch": flops, "ms_per_launch": stage_ms["pfn"], "kept_points": kept, "pillars": pillars}
+    bytes_tile = algorithmic_bytes_per_tile(N, args.workload)
+    per_gpu_gbs = bytes_tile * (value / world) / 1e9
+    hbm = {"bound": "hbm", "achieved": per_gpu_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu_gbs / hbm_peak,
+           "bytes_per_tile": bytes_tile, "peak_source": which, "scope": "whole path, per GPU"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        po2, cenc, cpe = cpu_oracle_modules(M)
+        n = min(B, 4)
+        tiles = host_tiles[0][:n]
+        imgs = torch.rand(n, 3, 224, 224)
+        cpu_step(po2, cenc, cpe, tiles[:1], imgs[:1], args.workload)
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+            cpu_step(po2, cenc, cpe, tiles, imgs, args.workload)
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": n * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{n} of {B} tiles x {reps} repetitions ({N} pts/tile); oracle = CPU restatement of the "
+                                  "reference path (open3d 0.19.0 not installable offline)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
+            "config": workload_config(args), "mpoints_per_s": value * N / 1e6,
+            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launch_mode": "cuda_graph" if graphs else "c_abi_per_step",
+            "roofline": roofline, "hbm_roofline": hbm, "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -165,6 +165,15 @@ int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, in
                     int32_t patch, const float* weight, const float* bias, int32_t channels, int32_t precision,
                     void* out, int32_t out_dtype, int32_t c_total, int32_t c_offset, void* stream);
 
+/*
+ * Measurement hooks (bench.py's roofline leg; no reference counterpart).  Between begin and end every
+ * p3p_encode call made by this thread records CUDA events around its two kernels on the caller's stream.
+ * p3p_profile_end synchronises those events and returns, per recorded call, the milliseconds of the
+ * voxelize kernel (incl. its counter memset) and of the PFN kernel (arrays of `capacity` floats, may be NULL).
+ */
+int p3p_profile_begin(int32_t max_records);
+int p3p_profile_end(float* ms_voxelize, float* ms_pfn, int32_t capacity, int32_t* num_records);
+
 #ifdef __cplusplus
 }
 #endif

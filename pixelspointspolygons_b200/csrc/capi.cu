@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "p3p_internal.cuh"
 
@@ -89,7 +90,7 @@ int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out)
     int64_t S = (total_points + denom - 1) / denom;
     S = (S + 255) / 256 * 256;
     if (S < 1024) S = 1024;
-    if (S > 8192) S = 8192;
+    if (S > kMaxChunkPoints) S = kMaxChunkPoints;
     l.chunk_points = (int)S;
     const int64_t mc = total_points / S + B;
     if (mc > 0x7fffffff) return fail(P3P_ERR_UNSUPPORTED, "too many ranking chunks");
@@ -101,7 +102,10 @@ int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out)
         return o;
     };
     const size_t HW = (size_t)g.ny * g.nx;
-    l.off_chunk_hist = take((size_t)l.max_chunks * g.num_keys * sizeof(uint16_t));
+    l.sync_bytes = (size_t)(1 + l.max_chunks + B) * sizeof(unsigned);
+    l.off_sync = take(l.sync_bytes);
+    l.key_stride = (g.num_keys + 7) / 8 * 8;
+    l.off_chunk_hist = take((size_t)l.max_chunks * l.key_stride * sizeof(uint16_t));
     l.off_totals = take((size_t)B * g.num_keys * sizeof(int32_t));
     l.off_slots = take((size_t)B * g.num_keys * g.M * sizeof(float4));
     l.off_pil_key = take((size_t)B * g.Vmax * sizeof(int32_t));
@@ -114,6 +118,14 @@ int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out)
     *out = l;
     return P3P_OK;
 }
+
+// per-thread profiling state (p3p_profile_begin / p3p_profile_end)
+struct Profile {
+    bool on = false;
+    int used = 0;
+    std::vector<cudaEvent_t> ev;  // 3 events per record: before voxelize, after voxelize, after PFN
+};
+static thread_local Profile g_prof;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -269,9 +281,49 @@ int p3p_encode(const float* points, int32_t point_stride, const int64_t* tile_of
     a.c_total = c_total;
     a.c_offset = c_offset;
     if (lidar_zero) return launch_zero_lidar(a, st);  // `x_lidar * 0.0` (early_fusion_vit.py:113-119)
+    cudaEvent_t* ev = nullptr;
+    if (g_prof.on && (size_t)(g_prof.used + 1) * 3 <= g_prof.ev.size()) ev = g_prof.ev.data() + (size_t)g_prof.used * 3;
+    if (ev) cudaEventRecord(ev[0], st);
     rc = launch_voxelize(points, point_stride, tile_offsets, num_tiles, total_points, g, l, ws, nullptr, st);
     if (rc) return rc;
-    return run_pfn(a, precision, st);
+    if (ev) cudaEventRecord(ev[1], st);
+    rc = run_pfn(a, precision, st);
+    if (ev) {
+        cudaEventRecord(ev[2], st);
+        ++g_prof.used;
+    }
+    return rc;
+}
+
+int p3p_profile_begin(int32_t max_records) {
+    if (max_records < 1 || max_records > 100000) return fail(P3P_ERR_INVALID_ARGUMENT, "max_records %d", max_records);
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.assign((size_t)max_records * 3, nullptr);
+    for (auto& e : g_prof.ev) P3P_CUDA_CHECK(cudaEventCreate(&e));
+    g_prof.used = 0;
+    g_prof.on = true;
+    return P3P_OK;
+}
+
+int p3p_profile_end(float* ms_voxelize, float* ms_pfn, int32_t capacity, int32_t* num_records) {
+    if (!g_prof.on) return fail(P3P_ERR_INVALID_ARGUMENT, "p3p_profile_end without p3p_profile_begin");
+    g_prof.on = false;
+    int n = g_prof.used < capacity ? g_prof.used : capacity;
+    float* dst[2] = {ms_voxelize, ms_pfn};
+    for (int i = 0; i < n; ++i) {
+        cudaEvent_t* e = g_prof.ev.data() + (size_t)i * 3;
+        P3P_CUDA_CHECK(cudaEventSynchronize(e[2]));
+        for (int s = 0; s < 2; ++s) {
+            float ms = 0.f;
+            P3P_CUDA_CHECK(cudaEventElapsedTime(&ms, e[s], e[s + 1]));
+            if (dst[s]) dst[s][i] = ms;
+        }
+    }
+    if (num_records) *num_records = n;
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear();
+    g_prof.used = 0;
+    return P3P_OK;
 }
 
 int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, int32_t height, int32_t width,

@@ -25,7 +25,7 @@ int fail(int code, const char* fmt, ...);
 // ----------------------------------------------------------------------------------------------
 constexpr int kFlagDropOverflow = P3P_GRID_DROP_OVERFLOW;  // DESIGN.md uncertainty ledger U1
 constexpr int kMaxKeys = 6144;        // smem histogram budget of the ranking kernels
-constexpr int kInvalidKey = 0xFFFF;   // uint16 key cache marker
+constexpr int kMaxChunkPoints = 4096; // points per ranking chunk held in registers (16 per lane x 256 threads)
 constexpr int kC0 = 32;               // feat_channels[0] / 2: width of PFN layer 0
 
 struct GridDev {
@@ -47,9 +47,12 @@ int make_grid(const p3p_grid* g, GridDev* out);
 // ----------------------------------------------------------------------------------------------
 struct WsLayout {
     int B;
-    int chunk_points;      // S: points per ranking chunk (multiple of 256)
-    int max_chunks;        // upper bound of the number of chunks over the batch
-    size_t off_chunk_hist; // uint16 [max_chunks][num_keys]
+    int chunk_points;      // S: points per ranking chunk (multiple of 256, <= kMaxChunkPoints)
+    int max_chunks;        // upper bound of the number of chunks over the batch (= grid of the voxelize kernel)
+    int key_stride;        // chunk_hist row stride (elements)
+    size_t off_sync;       // uint32 ticket, flags[max_chunks], tile_done[B]  (zeroed at the start of every call)
+    size_t sync_bytes;
+    size_t off_chunk_hist; // uint16 [max_chunks][key_stride]
     size_t off_totals;     // int32  [B][num_keys]   uncapped points per key
     size_t off_slots;      // float4 [B][num_keys][M] (x, y, z, bits(tile-local index)), rank order
     size_t off_pil_key;    // int32  [B][Vmax]       key of pillar r (voxel order, after both filters)
@@ -64,6 +67,9 @@ struct WsLayout {
 int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out);
 
 struct WsPtrs {
+    unsigned* sync;
+    int max_chunks;
+    int key_stride;  // row stride of chunk_hist in elements (num_keys rounded up to 8)
     uint16_t* chunk_hist;
     int32_t* totals;
     float4* slots;
@@ -78,6 +84,9 @@ struct WsPtrs {
 inline WsPtrs ws_ptrs(void* base, const WsLayout& l) {
     char* b = static_cast<char*>(base);
     WsPtrs p;
+    p.sync = reinterpret_cast<unsigned*>(b + l.off_sync);
+    p.max_chunks = l.max_chunks;
+    p.key_stride = l.key_stride;
     p.chunk_hist = reinterpret_cast<uint16_t*>(b + l.off_chunk_hist);
     p.totals = reinterpret_cast<int32_t*>(b + l.off_totals);
     p.slots = reinterpret_cast<float4*>(b + l.off_slots);
@@ -269,6 +278,11 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
             : "memory");
     }
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{.reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p;}" : "=r"(pred));
+    return pred != 0;
+}
 // K-major smem operand descriptor (cute::UMMA::SmemDescriptor, version 1): 8-row groups `sbo` bytes apart
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
     const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
@@ -287,6 +301,14 @@ __device__ __forceinline__ void tmem_ld64_wait(uint32_t taddr, float (&v)[64]) {
         "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];\n"
         "tcgen05.wait::ld.sync.aligned;\n"
         : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15]),"=f"(v[16]),"=f"(v[17]),"=f"(v[18]),"=f"(v[19]),"=f"(v[20]),"=f"(v[21]),"=f"(v[22]),"=f"(v[23]),"=f"(v[24]),"=f"(v[25]),"=f"(v[26]),"=f"(v[27]),"=f"(v[28]),"=f"(v[29]),"=f"(v[30]),"=f"(v[31]),"=f"(v[32]),"=f"(v[33]),"=f"(v[34]),"=f"(v[35]),"=f"(v[36]),"=f"(v[37]),"=f"(v[38]),"=f"(v[39]),"=f"(v[40]),"=f"(v[41]),"=f"(v[42]),"=f"(v[43]),"=f"(v[44]),"=f"(v[45]),"=f"(v[46]),"=f"(v[47]),"=f"(v[48]),"=f"(v[49]),"=f"(v[50]),"=f"(v[51]),"=f"(v[52]),"=f"(v[53]),"=f"(v[54]),"=f"(v[55]),"=f"(v[56]),"=f"(v[57]),"=f"(v[58]),"=f"(v[59]),"=f"(v[60]),"=f"(v[61]),"=f"(v[62]),"=f"(v[63])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t taddr, float (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15]),"=f"(v[16]),"=f"(v[17]),"=f"(v[18]),"=f"(v[19]),"=f"(v[20]),"=f"(v[21]),"=f"(v[22]),"=f"(v[23]),"=f"(v[24]),"=f"(v[25]),"=f"(v[26]),"=f"(v[27]),"=f"(v[28]),"=f"(v[29]),"=f"(v[30]),"=f"(v[31])
         : "r"(taddr)
         : "memory");
 }
@@ -318,6 +340,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+// packed fp32 FMA (FFMA2): two lanes per instruction
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

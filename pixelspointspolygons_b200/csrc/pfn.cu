@@ -90,6 +90,13 @@ __global__ void pfn_prepare_kernel(p3p_pfn_params p, int precision, char* blob, 
         front[7 * 32 + k] = w[5];                        // Wmz (multiplies mean_z)
         front[8 * 32 + k] = sh;                          // b0
         front[9 * 32 + k] = fmaxf(sh, 0.f);              // h_pad
+        if (precision == P3P_PRECISION_TF32) {
+            // kind::tf32 reads the upper 19 bits of each fp32 operand (truncation).  Layer 0 is positively homogeneous
+            // (relu of an affine map), so scaling all of it by (1 + 2^-12) makes that truncation a round-to-nearest
+            // of the unscaled h -- no conversion instruction per value in the kernel.
+            const float up = 1.0f + 0x1p-12f;
+            for (int r = 0; r < 10; ++r) front[r * 32 + k] *= up;
+        }
     }
     const bool tf32 = (precision != P3P_PRECISION_BF16);
     for (int c = tid; c < bl.Cpad; c += nthreads) {
@@ -261,9 +268,12 @@ __global__ void zero_lidar_kernel(PfnArgs a) {
 // ------------------------------------------------------------------------------------------------
 // tensor-core kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kTcThreads = 544;  // warp 0: TMEM alloc + MMA issue; warps 1-4: front end; warps 5-16: epilogue
-constexpr int kNS = 4;           // B-operand stages == pillar pairs per unit
-constexpr int kUnit = 8;         // items per unit (one 32-byte NCHW sector per channel)
+constexpr int kNF = 8;                         // front-end warps (one pillar each at a time)
+constexpr int kNS = kNF / 2;                   // B-operand stages: one pillar pair each
+constexpr int kEpiWarp0 = 1 + kNF;             // warp 0: TMEM alloc + MMA issue; 1..kNF: front end; then 12 epilogue warps
+constexpr int kTcThreads = 32 * (kEpiWarp0 + 12);
+constexpr int kUnit = 8;                       // items per epilogue flush (one 32-byte NCHW sector per channel)
+constexpr int kPairsPerUnit = kUnit / 2;
 constexpr int kTmemStage = 160;  // TMEM columns per channel tile: 128 (pair) + 16 (G), padded
 
 template <bool kTf32>
@@ -278,9 +288,17 @@ struct TcCfg {
     static constexpr int kGroup = kTf32 ? 4 : 8;          // channels per 16-byte operand chunk
     static constexpr int kGroups = 32 / kGroup;
     static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * (kHStage + kGStage);
-    static constexpr size_t kSmemFloats = 10 * 32 + 384 + 4 * 32;
-    static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + 16 * 8 + 16;
+    static constexpr size_t kSmemFloats = 10 * 32 + 384 + kNF * 32;
+    static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + (2 * kNS + 8) * 8 + 16;
 };
+
+__device__ __forceinline__ float max32(const float (&v)[32]) {
+    float r[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) r[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    r[10] = fmaxf(v[30], v[31]);
+    return fmaxf(fmax3(fmax3(r[0], r[1], r[2]), fmax3(r[3], r[4], r[5]), fmax3(r[6], r[7], r[8])), fmaxf(r[9], r[10]));
+}
 
 __device__ __forceinline__ float max64(const float (&v)[64]) {
     float r[22];
@@ -306,17 +324,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     unsigned char* sG = sH + kNS * Cfg::kHStage;
     float* sFront = reinterpret_cast<float*>(sG + kNS * Cfg::kGStage);  // [10][32]
     float* sB1 = sFront + 10 * 32;                                      // [384]
-    float* sKap = sB1 + 384;                                            // [4][32]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sKap + 4 * 32);
-    uint64_t* h_full = bars;        // [kNS] front end -> MMA (2 arrivals: the two warps of a pair)
-    uint64_t* h_empty = bars + 4;   // [kNS] MMA -> front end (tcgen05.commit)
-    uint64_t* t_full = bars + 8;    // [3]   MMA -> epilogue group m (tcgen05.commit)
-    uint64_t* t_empty = bars + 11;  // [3]   epilogue group m -> MMA (128 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    float* sKap = sB1 + 384;                                            // [kNF][32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sKap + kNF * 32);
+    uint64_t* h_full = bars;                 // [kNS] front end -> MMA (2 arrivals: the two warps of a pair)
+    uint64_t* h_empty = bars + kNS;          // [kNS] MMA -> front end (tcgen05.commit)
+    uint64_t* t_full = bars + 2 * kNS;       // [3]   MMA -> epilogue group m (tcgen05.commit)
+    uint64_t* t_empty = bars + 2 * kNS + 3;  // [3]   epilogue group m -> MMA (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int MT = a.bl.MT;
     const int64_t num_units = (a.num_items + kUnit - 1) / kUnit;
+    const int64_t my_units = (num_units > blockIdx.x) ? (num_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t my_pairs = my_units * kPairsPerUnit;  // pairs this CTA processes, in order p = 0, 1, ...
 
     // ---- one-time setup --------------------------------------------------------------------------
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -346,59 +366,67 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // =========================== MMA issuer (one thread) ===========================
-        if (lane == 0) {
-            const uint32_t idesc_main = make_idesc(kTf32, 128, 128);
-            const uint32_t idesc_g = make_idesc(kTf32, 128, 16);
-            const uint32_t aA1 = smem_u32(sA1), aA2 = smem_u32(sA2), aH = smem_u32(sH), aG = smem_u32(sG);
-            uint32_t gp = 0;
-            uint32_t ul = 0;
-            for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x, ++ul) {
-                for (int q = 0; q < kNS; ++q, ++gp) {
-                    mbar_wait(&h_full[q], ul & 1);
+        // =========================== MMA issuer ===========================
+        // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers);
+        // one elected lane issues the tcgen05 instructions and their commits.
+        const bool leader = elect_one();
+        const uint32_t idesc_main = make_idesc(kTf32, 128, 128);
+        const uint32_t idesc_g = make_idesc(kTf32, 128, 16);
+        const uint32_t desc_hi = (Cfg::kSBO >> 4) | (1u << 14) | (Cfg::kLayout << 29);
+        const uint32_t a1_lo = (smem_u32(sA1) >> 4) | (1u << 16), a2_lo = (smem_u32(sA2) >> 4) | (1u << 16);
+        const uint32_t h_lo = (smem_u32(sH) >> 4) | (1u << 16), g_lo = (smem_u32(sG) >> 4) | (1u << 16);
+        int st = 0;
+        uint32_t use = 0;
+        for (int64_t p = 0; p < my_pairs; ++p) {
+            mbar_wait(&h_full[st], use & 1);
+            tc_fence_after();
+            const uint32_t hs_lo = h_lo + (uint32_t)st * (Cfg::kHStage >> 4), gs_lo = g_lo + (uint32_t)st * (Cfg::kGStage >> 4);
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                if (m < MT) {
+                    mbar_wait(&t_empty[m], ((uint32_t)p & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t hs = aH + q * Cfg::kHStage, gs = aG + q * Cfg::kGStage;
-                    for (int m = 0; m < MT; ++m) {
-                        mbar_wait(&t_empty[m], (gp & 1) ^ 1);
-                        tc_fence_after();
+                    if (leader) {
                         const uint32_t d_main = tmem_base + m * kTmemStage, d_g = d_main + 128;
 #pragma unroll
                         for (int k = 0; k < Cfg::kKSteps; ++k)
-                            tc_mma<kTf32>(d_g, make_smem_desc(aA2 + m * Cfg::kATile + k * 32, Cfg::kSBO, Cfg::kLayout),
-                                          make_smem_desc(gs + k * 32, Cfg::kSBO, Cfg::kLayout), idesc_g, k > 0);
+                            tc_mma<kTf32>(d_g, ((uint64_t)desc_hi << 32) | (a2_lo + (uint32_t)((m * Cfg::kATile + k * 32) >> 4)),
+                                          ((uint64_t)desc_hi << 32) | (gs_lo + (uint32_t)(k * 2)), idesc_g, k > 0);
 #pragma unroll
                         for (int k = 0; k < Cfg::kKSteps; ++k)
-                            tc_mma<kTf32>(d_main, make_smem_desc(aA1 + m * Cfg::kATile + k * 32, Cfg::kSBO, Cfg::kLayout),
-                                          make_smem_desc(hs + k * 32, Cfg::kSBO, Cfg::kLayout), idesc_main, k > 0);
+                            tc_mma<kTf32>(d_main, ((uint64_t)desc_hi << 32) | (a1_lo + (uint32_t)((m * Cfg::kATile + k * 32) >> 4)),
+                                          ((uint64_t)desc_hi << 32) | (hs_lo + (uint32_t)(k * 2)), idesc_main, k > 0);
                         tc_commit(&t_full[m]);
                     }
-                    tc_commit(&h_empty[q]);
+                    __syncwarp();
                 }
             }
+            if (leader) tc_commit(&h_empty[st]);
+            __syncwarp();
+            if (++st == kNS) { st = 0; ++use; }
         }
-        __syncwarp();
-    } else if (warp <= 4) {
+    } else if (warp < kEpiWarp0) {
         // =========================== front end: one pillar per warp ===========================
-        const int fw = warp - 1, half = fw & 1, qbase = fw >> 1;
-        const float4* Ux4 = reinterpret_cast<const float4*>(sFront + 0 * 32);
-        const float4* Uy4 = reinterpret_cast<const float4*>(sFront + 1 * 32);
-        const float4* Uz4 = reinterpret_cast<const float4*>(sFront + 2 * 32);
+        const int fw = warp - 1, half = fw & 1, st = fw >> 1;  // this warp fills half `half` of stage `st`
+        const float2* Ux2 = reinterpret_cast<const float2*>(sFront + 0 * 32);
+        const float2* Uy2 = reinterpret_cast<const float2*>(sFront + 1 * 32);
+        const float2* Uz2 = reinterpret_cast<const float2*>(sFront + 2 * 32);
         const float4* Hp4 = reinterpret_cast<const float4*>(sFront + 9 * 32);
         float* kap = sKap + fw * 32;
-        const float4* Kp4 = reinterpret_cast<const float4*>(kap);
+        const float2* Kp2 = reinterpret_cast<const float2*>(kap);
         const float kcx = sFront[3 * 32 + lane], kcy = sFront[4 * 32 + lane];
         const float wmx = sFront[5 * 32 + lane], wmy = sFront[6 * 32 + lane], wmz = sFront[7 * 32 + lane];
         const float b0l = sFront[8 * 32 + lane];
 
-        // software pipeline over this warp's item sequence: descriptor two ahead, points one ahead
-        // sequence index s -> unit = blockIdx.x + (s / 2) * gridDim.x, pair q = qbase + 2 * (s & 1)
-        auto item_of = [&](int64_t s) -> int64_t {
-            const int64_t u = blockIdx.x + (s >> 1) * (int64_t)gridDim.x;
-            if (u >= num_units) return a.num_items;  // fetch_item -> invalid
-            return u * kUnit + (qbase + 2 * (int)(s & 1)) * 2 + half;
+        // this warp's pairs: p = st, st + kNS, ...; pair p covers items 2p, 2p+1 of the CTA's unit sequence
+        auto item_of = [&](int64_t j) -> int64_t {
+            const int64_t p = st + j * kNS;
+            if (p >= my_pairs) return a.num_items;  // fetch_item -> invalid
+            const int64_t u = blockIdx.x + (p / kPairsPerUnit) * (int64_t)gridDim.x;
+            return u * kUnit + (p % kPairsPerUnit) * 2 + half;
         };
-        const int64_t my_units = (num_units > blockIdx.x) ? (num_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const int64_t nseq = my_units * 2;
+        const int64_t nseq = (my_pairs > st) ? (my_pairs - st + kNS - 1) / kNS : 0;
+        // software pipeline: descriptor two ahead, points one ahead
         Item it_cur = fetch_item(a, item_of(0));
         Item it_nxt = fetch_item(a, item_of(1));
         float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
@@ -407,10 +435,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             if (lane < it_cur.n) c0 = sl[lane];
             if (lane + 32 < it_cur.n) c1 = sl[lane + 32];
         }
-        for (int64_t s = 0; s < nseq; ++s) {
+        unsigned char* hst = sH + st * Cfg::kHStage;
+        unsigned char* gst = sG + st * Cfg::kGStage;
+        const int R0 = half * 64 + lane, R1 = R0 + 32;
+        for (int64_t j = 0; j < nseq; ++j) {
             const Item it = it_cur;
             const float4 p0 = c0, p1 = c1;
-            // prefetch: points of s+1, descriptor of s+2
             it_cur = it_nxt;
             c0 = make_float4(0.f, 0.f, 0.f, 0.f); c1 = c0;
             if (it_cur.valid) {
@@ -418,11 +448,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                 if (lane < it_cur.n) c0 = sl[lane];
                 if (lane + 32 < it_cur.n) c1 = sl[lane + 32];
             }
-            it_nxt = fetch_item(a, item_of(s + 2));
+            it_nxt = fetch_item(a, item_of(j + 2));
 
-            const uint32_t ul = (uint32_t)(s >> 1);
-            const int q = qbase + 2 * (int)(s & 1);
-            mbar_wait(&h_empty[q], (ul & 1) ^ 1);
+            mbar_wait(&h_empty[st], ((uint32_t)j & 1) ^ 1);
             if (it.valid) {
                 const int n = it.n;
                 const float sx = warp_sum(p0.x + p1.x), sy = warp_sum(p0.y + p1.y), sz = warp_sum(p0.z + p1.z);
@@ -436,60 +464,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                 kv = __fmaf_rn(-wmz, mz, kv);
                 kap[lane] = kv;
                 __syncwarp();
-                const float x0 = p0.x - it.ctr_x, y0 = p0.y - it.ctr_y, z0 = p0.z;
-                const float x1 = p1.x - it.ctr_x, y1 = p1.y - it.ctr_y, z1 = p1.z;
+                const float2 x0 = make_float2(p0.x - it.ctr_x, p0.x - it.ctr_x), y0 = make_float2(p0.y - it.ctr_y, p0.y - it.ctr_y);
+                const float2 z0 = make_float2(p0.z, p0.z);
+                const float2 x1 = make_float2(p1.x - it.ctr_x, p1.x - it.ctr_x), y1 = make_float2(p1.y - it.ctr_y, p1.y - it.ctr_y);
+                const float2 z1 = make_float2(p1.z, p1.z);
                 const bool ok0 = lane < n, ok1 = lane + 32 < n;
-                const int R0 = half * 64 + lane, R1 = R0 + 32;
-                unsigned char* hst = sH + q * Cfg::kHStage;
-                unsigned char* gst = sG + q * Cfg::kGStage;
 #pragma unroll
-                for (int j = 0; j < Cfg::kGroups; ++j) {
+                for (int g = 0; g < Cfg::kGroups; ++g) {
                     float h0[Cfg::kGroup], h1[Cfg::kGroup], hm[Cfg::kGroup];
 #pragma unroll
-                    for (int v4 = 0; v4 < Cfg::kGroup / 4; ++v4) {
-                        const int i4 = j * (Cfg::kGroup / 4) + v4;
-                        const float4 ux = Ux4[i4], uy = Uy4[i4], uz = Uz4[i4], kp = Kp4[i4];
-                        h0[v4 * 4 + 0] = fmaxf(__fmaf_rn(ux.x, x0, __fmaf_rn(uy.x, y0, __fmaf_rn(uz.x, z0, kp.x))), 0.f);
-                        h0[v4 * 4 + 1] = fmaxf(__fmaf_rn(ux.y, x0, __fmaf_rn(uy.y, y0, __fmaf_rn(uz.y, z0, kp.y))), 0.f);
-                        h0[v4 * 4 + 2] = fmaxf(__fmaf_rn(ux.z, x0, __fmaf_rn(uy.z, y0, __fmaf_rn(uz.z, z0, kp.z))), 0.f);
-                        h0[v4 * 4 + 3] = fmaxf(__fmaf_rn(ux.w, x0, __fmaf_rn(uy.w, y0, __fmaf_rn(uz.w, z0, kp.w))), 0.f);
-                        h1[v4 * 4 + 0] = fmaxf(__fmaf_rn(ux.x, x1, __fmaf_rn(uy.x, y1, __fmaf_rn(uz.x, z1, kp.x))), 0.f);
-                        h1[v4 * 4 + 1] = fmaxf(__fmaf_rn(ux.y, x1, __fmaf_rn(uy.y, y1, __fmaf_rn(uz.y, z1, kp.y))), 0.f);
-                        h1[v4 * 4 + 2] = fmaxf(__fmaf_rn(ux.z, x1, __fmaf_rn(uy.z, y1, __fmaf_rn(uz.z, z1, kp.z))), 0.f);
-                        h1[v4 * 4 + 3] = fmaxf(__fmaf_rn(ux.w, x1, __fmaf_rn(uy.w, y1, __fmaf_rn(uz.w, z1, kp.w))), 0.f);
-                        if (n < 64) {  // padded slots carry relu(BN(0)) (warp-uniform branch)
-                            const float4 hp = Hp4[i4];
+                    for (int v2 = 0; v2 < Cfg::kGroup / 2; ++v2) {
+                        const int i2 = g * (Cfg::kGroup / 2) + v2;
+                        const float2 ux = Ux2[i2], uy = Uy2[i2], uz = Uz2[i2], kp = Kp2[i2];
+                        const float2 a0 = ffma2(ux, x0, ffma2(uy, y0, ffma2(uz, z0, kp)));
+                        const float2 a1 = ffma2(ux, x1, ffma2(uy, y1, ffma2(uz, z1, kp)));
+                        h0[v2 * 2 + 0] = fmaxf(a0.x, 0.f); h0[v2 * 2 + 1] = fmaxf(a0.y, 0.f);
+                        h1[v2 * 2 + 0] = fmaxf(a1.x, 0.f); h1[v2 * 2 + 1] = fmaxf(a1.y, 0.f);
+                    }
+                    if (n < 64) {  // padded slots carry relu(BN(0)) (warp-uniform branch)
+#pragma unroll
+                        for (int v4 = 0; v4 < Cfg::kGroup / 4; ++v4) {
+                            const float4 hp = Hp4[g * (Cfg::kGroup / 4) + v4];
                             if (!ok0) { h0[v4 * 4 + 0] = hp.x; h0[v4 * 4 + 1] = hp.y; h0[v4 * 4 + 2] = hp.z; h0[v4 * 4 + 3] = hp.w; }
                             if (!ok1) { h1[v4 * 4 + 0] = hp.x; h1[v4 * 4 + 1] = hp.y; h1[v4 * 4 + 2] = hp.z; h1[v4 * 4 + 3] = hp.w; }
                         }
                     }
 #pragma unroll
                     for (int i = 0; i < Cfg::kGroup; ++i) hm[i] = warp_max_f32(fmaxf(h0[i], h1[i]));
-                    uint4 w0v, w1v, wmv;
                     if constexpr (kTf32) {
-                        w0v = make_uint4(to_tf32(h0[0]), to_tf32(h0[1]), to_tf32(h0[2]), to_tf32(h0[3]));
-                        w1v = make_uint4(to_tf32(h1[0]), to_tf32(h1[1]), to_tf32(h1[2]), to_tf32(h1[3]));
-                        wmv = make_uint4(to_tf32(hm[0]), to_tf32(hm[1]), to_tf32(hm[2]), to_tf32(hm[3]));
-                        *reinterpret_cast<uint4*>(hst + R0 * 128 + ((j ^ (R0 & 7)) * 16)) = w0v;
-                        *reinterpret_cast<uint4*>(hst + R1 * 128 + ((j ^ (R1 & 7)) * 16)) = w1v;
-                        if (lane == 0) *reinterpret_cast<uint4*>(gst + half * 128 + ((j ^ half) * 16)) = wmv;
+                        // operands are already scaled by (1 + 2^-12): the MMA's truncation rounds them to nearest tf32
+                        *reinterpret_cast<float4*>(hst + R0 * 128 + ((g ^ (R0 & 7)) * 16)) = make_float4(h0[0], h0[1], h0[2], h0[3]);
+                        *reinterpret_cast<float4*>(hst + R1 * 128 + ((g ^ (R1 & 7)) * 16)) = make_float4(h1[0], h1[1], h1[2], h1[3]);
+                        if (lane == 0) *reinterpret_cast<float4*>(gst + half * 128 + ((g ^ half) * 16)) = make_float4(hm[0], hm[1], hm[2], hm[3]);
                     } else {
-                        w0v = make_uint4(pack_bf16(h0[0], h0[1]), pack_bf16(h0[2], h0[3]), pack_bf16(h0[4], h0[5]), pack_bf16(h0[6], h0[7]));
-                        w1v = make_uint4(pack_bf16(h1[0], h1[1]), pack_bf16(h1[2], h1[3]), pack_bf16(h1[4], h1[5]), pack_bf16(h1[6], h1[7]));
-                        wmv = make_uint4(pack_bf16(hm[0], hm[1]), pack_bf16(hm[2], hm[3]), pack_bf16(hm[4], hm[5]), pack_bf16(hm[6], hm[7]));
-                        *reinterpret_cast<uint4*>(hst + R0 * 64 + ((j ^ ((R0 >> 1) & 3)) * 16)) = w0v;
-                        *reinterpret_cast<uint4*>(hst + R1 * 64 + ((j ^ ((R1 >> 1) & 3)) * 16)) = w1v;
-                        if (lane == 0) *reinterpret_cast<uint4*>(gst + half * 64 + (j * 16)) = wmv;
+                        const uint4 w0v = make_uint4(pack_bf16(h0[0], h0[1]), pack_bf16(h0[2], h0[3]), pack_bf16(h0[4], h0[5]), pack_bf16(h0[6], h0[7]));
+                        const uint4 w1v = make_uint4(pack_bf16(h1[0], h1[1]), pack_bf16(h1[2], h1[3]), pack_bf16(h1[4], h1[5]), pack_bf16(h1[6], h1[7]));
+                        const uint4 wmv = make_uint4(pack_bf16(hm[0], hm[1]), pack_bf16(hm[2], hm[3]), pack_bf16(hm[4], hm[5]), pack_bf16(hm[6], hm[7]));
+                        *reinterpret_cast<uint4*>(hst + R0 * 64 + ((g ^ ((R0 >> 1) & 3)) * 16)) = w0v;
+                        *reinterpret_cast<uint4*>(hst + R1 * 64 + ((g ^ ((R1 >> 1) & 3)) * 16)) = w1v;
+                        if (lane == 0) *reinterpret_cast<uint4*>(gst + half * 64 + (g * 16)) = wmv;
                     }
                 }
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&h_full[q]);
+            if (lane == 0) mbar_arrive(&h_full[st]);
         }
     } else {
         // =========================== epilogue: warp group m owns channel tile m ===========================
-        const int m = (warp - 5) >> 2;
+        const int m = (warp - kEpiWarp0) >> 2;
         const int quad = warp & 3;  // TMEM lanes this warp may read: 32 * (warp id % 4)
         const int c = m * 128 + quad * 32 + lane;
         if (m < MT) {
@@ -518,14 +541,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                     vmask |= (v ? 1u : 0u) << i;
                 }
 #pragma unroll
-                for (int q = 0; q < kNS; ++q, ++gp) {
+                for (int q = 0; q < kPairsPerUnit; ++q, ++gp) {
                     mbar_wait(&t_full[m], gp & 1);
                     tc_fence_after();
-                    float v[64];
-                    tmem_ld64_wait(taddr + 0, v);
-                    const float mA = max64(v);
-                    tmem_ld64_wait(taddr + 64, v);
-                    const float mB = max64(v);
+                    float v[32];
+                    tmem_ld32_wait(taddr + 0, v);
+                    float mA = max32(v);
+                    tmem_ld32_wait(taddr + 32, v);
+                    mA = fmaxf(mA, max32(v));
+                    tmem_ld32_wait(taddr + 64, v);
+                    float mB = max32(v);
+                    tmem_ld32_wait(taddr + 96, v);
+                    mB = fmaxf(mB, max32(v));
                     float gA, gB;
                     tmem_ld2_wait(taddr + 128, gA, gB);
                     tc_fence_before();
