@@ -2,7 +2,7 @@
 # one optimisation iteration on the GPU box: parity suite, bench (tf32, bf16), ncu launch list + full captures
 set -u
 mkdir -p gpurun_out
-T="timeout 900"
+T="timeout 600"
 $T python -m pytest tests -q -m gpu -x -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -n 6 gpurun_out/pytest_gpu.log
 $T python bench.py --steps 200 --warmup 20 > gpurun_out/bench_tf32.json 2> gpurun_out/bench_tf32.err; echo "bench exit $?"
 $T python bench.py --steps 200 --warmup 20 --precision bf16 --no-cpu-baseline > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err
