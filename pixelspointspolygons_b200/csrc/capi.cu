@@ -75,6 +75,14 @@ int make_grid(const p3p_grid* g, GridDev* out) {
     d.vy = g->voxel_size[1];
     d.x_off = g->voxel_size[0] / 2 + g->range_min[0];
     d.y_off = g->voxel_size[1] / 2 + g->range_min[1];
+    // fixed-point grid of the cluster-mean sums: |coordinate| * 2^k < 2^30, k <= 20
+    float maxabs = 1.f;
+    for (int i = 0; i < 3; ++i) maxabs = fmaxf(maxabs, fmaxf(fabsf(g->range_min[i]), fabsf(g->range_max[i])));
+    int k = 30 - (int)ceilf(log2f(maxabs + 1.f));
+    if (k > 20) k = 20;
+    if (k < 0) return fail(P3P_ERR_UNSUPPORTED, "point_cloud_range magnitude %g too large", (double)maxabs);
+    d.fix_scale = ldexpf(1.f, k);
+    d.fix_inv = ldexpf(1.f, -k);
     *out = d;
     return P3P_OK;
 }
@@ -102,8 +110,10 @@ int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out)
         return o;
     };
     const size_t HW = (size_t)g.ny * g.nx;
-    l.sync_bytes = (size_t)(1 + l.max_chunks + B) * sizeof(unsigned);
+    const size_t sync_words = ((size_t)(1 + l.max_chunks + B) * sizeof(unsigned) + 15) / 16 * 16;
+    l.sync_bytes = sync_words + (size_t)B * g.num_keys;  // ticket / flags / tile_done, then the edge flags: one memset
     l.off_sync = take(l.sync_bytes);
+    l.off_edge = l.off_sync + sync_words;
     l.key_stride = (g.num_keys + 7) / 8 * 8;
     l.off_chunk_hist = take((size_t)l.max_chunks * l.key_stride * sizeof(uint16_t));
     l.off_totals = take((size_t)B * g.num_keys * sizeof(int32_t));
@@ -112,6 +122,7 @@ int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out)
     l.off_pil_n = take((size_t)B * g.Vmax * sizeof(int32_t));
     l.off_pil_coord = take((size_t)B * g.Vmax * sizeof(int32_t));
     l.off_num_pil = take((size_t)B * sizeof(int32_t));
+    l.off_tile_hi = take((size_t)B * sizeof(int32_t));
     l.off_owner = take((size_t)B * HW * sizeof(int32_t));
     l.off_cell_desc = take((size_t)B * HW * sizeof(int32_t));
     l.total_bytes = off;
@@ -209,7 +220,7 @@ int p3p_voxelize(const float* points, int32_t point_stride, const int64_t* tile_
     if (rc) return rc;
     if (num_tiles == 0) return P3P_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = launch_voxelize(points, point_stride, tile_offsets, num_tiles, total_points, g, l, ws, out ? out->point_hash : nullptr, st);
+    rc = launch_voxelize(points, point_stride, tile_offsets, num_tiles, total_points, g, l, ws, out ? out->point_hash : nullptr, 1, st);
     if (rc) return rc;
     if (out) return launch_export(g, num_tiles, ws, out, st);
     return P3P_OK;
@@ -284,7 +295,7 @@ int p3p_encode(const float* points, int32_t point_stride, const int64_t* tile_of
     cudaEvent_t* ev = nullptr;
     if (g_prof.on && (size_t)(g_prof.used + 1) * 3 <= g_prof.ev.size()) ev = g_prof.ev.data() + (size_t)g_prof.used * 3;
     if (ev) cudaEventRecord(ev[0], st);
-    rc = launch_voxelize(points, point_stride, tile_offsets, num_tiles, total_points, g, l, ws, nullptr, st);
+    rc = launch_voxelize(points, point_stride, tile_offsets, num_tiles, total_points, g, l, ws, nullptr, 0, st);
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[1], st);
     rc = run_pfn(a, precision, st);

@@ -38,6 +38,7 @@ struct GridDev {
     int M, Vmax, ny, nx;
     int flags;
     float vx, vy, x_off, y_off;  // PillarFeatureNet: vx, vy, vx/2 + min_x, vy/2 + min_y
+    float fix_scale, fix_inv;    // fixed-point grid of the cluster-mean sums (2^k, 2^-k): order-independent, exact
 };
 
 int make_grid(const p3p_grid* g, GridDev* out);
@@ -50,15 +51,19 @@ struct WsLayout {
     int chunk_points;      // S: points per ranking chunk (multiple of 256, <= kMaxChunkPoints)
     int max_chunks;        // upper bound of the number of chunks over the batch (= grid of the voxelize kernel)
     int key_stride;        // chunk_hist row stride (elements)
-    size_t off_sync;       // uint32 ticket, flags[max_chunks], tile_done[B]  (zeroed at the start of every call)
-    size_t sync_bytes;
+    size_t off_sync;       // uint32 ticket, flags[max_chunks], tile_done[B], then uint8 edge[B][num_keys]
+    size_t sync_bytes;     //   (one block, zeroed at the start of every call)
+    size_t off_edge;       // uint8 [B][num_keys]: the run of this key holds a point on the x / y max face (cell == extent),
+                           //   i.e. its coordinates are not decodable from the key (hash aliasing)
     size_t off_chunk_hist; // uint16 [max_chunks][key_stride]
     size_t off_totals;     // int32  [B][num_keys]   uncapped points per key
-    size_t off_slots;      // float4 [B][num_keys][M] (x, y, z, bits(tile-local index)), rank order
+    size_t off_slots;      // float4 [B][num_keys][M] (x, y, z, bits(tile-local index)): the min(count, M) lowest-index
+                           //   points of the key, in no particular order
     size_t off_pil_key;    // int32  [B][Vmax]       key of pillar r (voxel order, after both filters)
     size_t off_pil_n;      // int32  [B][Vmax]       min(count, M)
     size_t off_pil_coord;  // int32  [B][Vmax]       cx | cy << 10 | cz << 20
     size_t off_num_pil;    // int32  [B]
+    size_t off_tile_hi;    // int32  [B]             bit 0: keys beyond the regular cells in use; bit 1: owner table written without a plan
     size_t off_owner;      // int32  [B][ny*nx]      voxel ordinal owning the canvas cell, -1 = empty
     size_t off_cell_desc;  // int32  [B][ny*nx]      key | n << 16 of the owning pillar, -1 = empty
     size_t total_bytes;
@@ -71,12 +76,14 @@ struct WsPtrs {
     int max_chunks;
     int key_stride;  // row stride of chunk_hist in elements (num_keys rounded up to 8)
     uint16_t* chunk_hist;
+    uint8_t* edge;
     int32_t* totals;
     float4* slots;
     int32_t* pil_key;
     int32_t* pil_n;
     int32_t* pil_coord;
     int32_t* num_pil;
+    int32_t* tile_hi;
     int32_t* owner;
     int32_t* cell_desc;
 };
@@ -88,12 +95,14 @@ inline WsPtrs ws_ptrs(void* base, const WsLayout& l) {
     p.max_chunks = l.max_chunks;
     p.key_stride = l.key_stride;
     p.chunk_hist = reinterpret_cast<uint16_t*>(b + l.off_chunk_hist);
+    p.edge = reinterpret_cast<uint8_t*>(b + l.off_edge);
     p.totals = reinterpret_cast<int32_t*>(b + l.off_totals);
     p.slots = reinterpret_cast<float4*>(b + l.off_slots);
     p.pil_key = reinterpret_cast<int32_t*>(b + l.off_pil_key);
     p.pil_n = reinterpret_cast<int32_t*>(b + l.off_pil_n);
     p.pil_coord = reinterpret_cast<int32_t*>(b + l.off_pil_coord);
     p.num_pil = reinterpret_cast<int32_t*>(b + l.off_num_pil);
+    p.tile_hi = reinterpret_cast<int32_t*>(b + l.off_tile_hi);
     p.owner = reinterpret_cast<int32_t*>(b + l.off_owner);
     p.cell_desc = reinterpret_cast<int32_t*>(b + l.off_cell_desc);
     return p;
@@ -140,7 +149,7 @@ struct PfnArgs {
 
 // launchers (host) ---------------------------------------------------------------------------------
 int launch_voxelize(const float* pts, int stride, const int64_t* offsets, int B, int64_t total, const GridDev& g,
-                    const WsLayout& l, const WsPtrs& ws, int32_t* point_hash, cudaStream_t st);
+                    const WsLayout& l, const WsPtrs& ws, int32_t* point_hash, int need_plan, cudaStream_t st);
 int launch_export(const GridDev& g, int B, const WsPtrs& ws, const p3p_voxel_outputs* out, cudaStream_t st);
 int launch_pfn_prepare(const p3p_pfn_params* p, int precision, char* blob, const BlobLayout& bl, cudaStream_t st);
 int launch_pfn_simt(const PfnArgs& a, cudaStream_t st);
@@ -159,15 +168,19 @@ int device_sm_count();
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // cell hash of one point, or -1 (Open3D VoxelizeCPU HashFn; fp32 subtract then multiply, truncation)
-__device__ __forceinline__ int point_key(const GridDev& g, float x, float y, float z) {
+// `edge` is set when the point sits on the x or y max face (cell index == extent): only such points make a hash
+// ambiguous (cx == ext_x aliases (0, cy + 1); cy == ext_y aliases (cx, 0, cz + 1)).
+__device__ __forceinline__ int point_key(const GridDev& g, float x, float y, float z, bool& edge) {
     const bool valid = (x >= g.mn[0]) && (x <= g.mx[0]) && (y >= g.mn[1]) && (y <= g.mx[1]) && (z >= g.mn[2]) &&
                        (z <= g.mx[2]);
+    edge = false;
     if (!valid) return -1;
     const int cx = __float2int_rz(__fmul_rn(__fsub_rn(x, g.mn[0]), g.inv[0]));
     const int cy = __float2int_rz(__fmul_rn(__fsub_rn(y, g.mn[1]), g.inv[1]));
     const int cz = __float2int_rz(__fmul_rn(__fsub_rn(z, g.mn[2]), g.inv[2]));
     const int h = cx + cy * g.stride1 + cz * g.stride2;
     if ((g.flags & kFlagDropOverflow) && h >= g.num_cells) return -1;
+    edge = (cx >= g.ext[0]) || (cy >= g.ext[1]);
     return h;
 }
 
@@ -349,6 +362,16 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
         : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
           "l"(*reinterpret_cast<unsigned long long*>(&c)));
     return *reinterpret_cast<float2*>(&d);
+}
+// Cluster-mean sums on a fixed-point grid: q = rn(v * 2^k), |q| < 2^30, summed exactly as two 16-bit halves
+// (<= 1024 terms each) -- independent of the order of the slots, hence bitwise reproducible.
+__device__ __forceinline__ void fix_split(float v, float scale, int& lo, int& hi) {
+    const int q = __float2int_rn(v * scale);
+    lo = q & 0xFFFF;
+    hi = q >> 16;
+}
+__device__ __forceinline__ float fix_mean(int sum_lo, int sum_hi, float inv_scale, float n) {
+    return __fdiv_rn(__fmaf_rn((float)sum_hi, 65536.0f, (float)sum_lo) * inv_scale, n);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

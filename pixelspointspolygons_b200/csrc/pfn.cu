@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(kSimtThreads) pfn_simt_kernel(PfnArgs a) {
     float* H = smem_f;                                  // [(M + 1)][kHStride]
     float* w0s = H + (size_t)(a.g.M + 1) * kHStride;    // [32][8]
     float* b0s = w0s + 256;                             // [32]
-    float* red = b0s + 32;                              // [4][3]
-    int* hmax_bits = reinterpret_cast<int*>(red + 12);  // [32]
+    int* red = reinterpret_cast<int*>(b0s + 32);        // [4][6] fixed-point partial sums
+    int* hmax_bits = red + 24;                          // [32]
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const float* w0g = reinterpret_cast<const float*>(a.blob + a.bl.off_w0);
@@ -175,20 +175,27 @@ __global__ void __launch_bounds__(kSimtThreads) pfn_simt_kernel(PfnArgs a) {
         }
         const float4* slot = item_slots(a, it);
         const int n = it.n;
-        // cluster mean over the kept points (padded slots are zeros in the reference's sum)
-        float sx = 0.f, sy = 0.f, sz = 0.f;
+        // cluster mean over the kept points (padded slots are zeros in the reference's sum), on the fixed-point grid
+        int sl[3] = {0, 0, 0}, sh[3] = {0, 0, 0};
         for (int r = tid; r < n; r += kSimtThreads) {
             const float4 p = slot[r];
-            sx += p.x; sy += p.y; sz += p.z;
+            int lo, hi;
+            fix_split(p.x, a.g.fix_scale, lo, hi); sl[0] += lo; sh[0] += hi;
+            fix_split(p.y, a.g.fix_scale, lo, hi); sl[1] += lo; sh[1] += hi;
+            fix_split(p.z, a.g.fix_scale, lo, hi); sl[2] += lo; sh[2] += hi;
         }
-        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-        if (lane == 0) { red[w * 3 + 0] = sx; red[w * 3 + 1] = sy; red[w * 3 + 2] = sz; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            sl[i] = __reduce_add_sync(0xffffffffu, sl[i]);
+            sh[i] = __reduce_add_sync(0xffffffffu, sh[i]);
+            if (lane == 0) { red[w * 6 + i] = sl[i]; red[w * 6 + 3 + i] = sh[i]; }
+        }
         if (tid < 32) hmax_bits[tid] = 0;
         __syncthreads();
         const float fn = (float)n;
-        const float mx = __fdiv_rn(red[0] + red[3] + red[6] + red[9], fn);
-        const float my = __fdiv_rn(red[1] + red[4] + red[7] + red[10], fn);
-        const float mz = __fdiv_rn(red[2] + red[5] + red[8] + red[11], fn);
+        const float mx = fix_mean(red[0] + red[6] + red[12] + red[18], red[3] + red[9] + red[15] + red[21], a.g.fix_inv, fn);
+        const float my = fix_mean(red[1] + red[7] + red[13] + red[19], red[4] + red[10] + red[16] + red[22], a.g.fix_inv, fn);
+        const float mz = fix_mean(red[2] + red[8] + red[14] + red[20], red[5] + red[11] + red[17] + red[23], a.g.fix_inv, fn);
 
         float hm[32];
 #pragma unroll
@@ -453,9 +460,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             mbar_wait(&h_empty[st], ((uint32_t)j & 1) ^ 1);
             if (it.valid) {
                 const int n = it.n;
-                const float sx = warp_sum(p0.x + p1.x), sy = warp_sum(p0.y + p1.y), sz = warp_sum(p0.z + p1.z);
-                const float fn = (float)n;
-                const float mpx = __fdiv_rn(sx, fn) - it.ctr_x, mpy = __fdiv_rn(sy, fn) - it.ctr_y, mz = __fdiv_rn(sz, fn);
+                float mean3[3];
+                {
+                    const float c0v[3] = {p0.x, p0.y, p0.z}, c1v[3] = {p1.x, p1.y, p1.z};
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {  // padded lanes hold zeros
+                        int l0, h0, l1, h1;
+                        fix_split(c0v[i], a.g.fix_scale, l0, h0);
+                        fix_split(c1v[i], a.g.fix_scale, l1, h1);
+                        mean3[i] = fix_mean(__reduce_add_sync(0xffffffffu, l0 + l1), __reduce_add_sync(0xffffffffu, h0 + h1),
+                                            a.g.fix_inv, (float)n);
+                    }
+                }
+                const float mpx = mean3[0] - it.ctr_x, mpy = mean3[1] - it.ctr_y, mz = mean3[2];
                 float kv = b0l;
                 kv = __fmaf_rn(kcx, it.ctr_x, kv);
                 kv = __fmaf_rn(kcy, it.ctr_y, kv);
@@ -603,7 +620,7 @@ int launch_pfn_prepare(const p3p_pfn_params* p, int precision, char* blob, const
 
 int launch_pfn_simt(const PfnArgs& a, cudaStream_t st) {
     if (a.num_items <= 0) return P3P_OK;
-    const size_t smem = ((size_t)(a.g.M + 1) * kHStride + 256 + 32 + 12 + 32) * sizeof(float);
+    const size_t smem = ((size_t)(a.g.M + 1) * kHStride + 256 + 32 + 24 + 32) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
         P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -3,28 +3,52 @@
 // Replaces the per-sample Python loop of Open3D-ML PointPillars.voxelize that the reference calls at
 // R:pixelspointspolygons/models/pointpillars/pointpillars_o3d.py:92.
 //
-// The reference sorts (hash, index) pairs per tile and keeps the first M indices of each run.  Only the stable
-// rank of a point inside its run matters, and only ranks < M survive, so nothing is sorted here:
+// The reference sorts (hash, index) pairs per tile and keeps the first M indices of each run.  What the rest of the
+// path consumes is, per key, the SET of its min(count, M) lowest-index points (the PFN is a max and an exact
+// fixed-point mean over that set), so nothing is sorted here:
 //
 //   * a CTA takes a ticket (atomic counter) -> chunk of <= 4096 consecutive points of one tile.  Tickets, not
 //     blockIdx, order the chunks, so a CTA only ever waits for CTAs that are already running.
-//   * every lane loads its <= 16 points into registers up front (all loads in flight at once; the xyz stream is
-//     read from HBM exactly once) and computes the cell hash with the reference's fp32 operation order.
-//   * each warp owns a contiguous segment of the chunk and counts it per key in a private shared-memory histogram
-//     (match.any aggregation, no atomics); the chunk's per-key counts are published to global memory and a flag
-//     is released.
-//   * the CTA acquires the flags of the earlier chunks of its tile, sums their counts per key (exclusive prefix
-//     over chunks, then over its own warps) and walks its registers again in index order:
-//     rank = base + (same-key lanes below me); survivors (rank < M) go to slots[tile][key][rank] =
-//     (x, y, z, tile-local index).  Deterministic: no atomics on the data path, no dependence on scheduling.
+//   * every lane hashes its <= 16 points (all loads in flight at once) with the reference's fp32 operation order;
+//     only the packed (key, rank) word of a point stays in a register.
+//   * each warp owns a contiguous segment of the chunk and counts it per key in a private shared-memory histogram,
+//     32 consecutive points per step: read count, write (count + 1 | lane tag), read back; the lane whose tag
+//     survived owns that count, the (rare) same-key losers of the step retry.  No atomics, no match.any.
+//   * the chunk's per-key counts are published to global memory and a flag is released; the CTA acquires the flags
+//     of the earlier chunks of its tile, sums their counts per key (exclusive prefix over chunks, then over its own
+//     warps) and walks its registers again: rank = base + rank-in-segment; survivors (rank < M) re-read their xyz
+//     (L1/L2 hit) and go to slots[tile][key][rank].  Inside one step same-key lanes hold their ranks in arbitrary
+//     order, which only matters in the step where the key crosses M: that step re-ranks in lane order
+//     (match.any, about 1 % of the steps).  The kept set is therefore exactly the reference's; the order inside a
+//     pillar is not (export_kernel sorts by index for the parity surface).
 //   * the last CTA of a tile to finish runs the tile's plan: keys in ascending order -> run ordinal (max_voxels
-//     cut), cell coordinates from the rank-0 (lowest index) point, x/y bound filter, final voxel order, and the
-//     canvas owner table (last pillar in voxel order wins a cell, Appendix A.5).
+//     cut), cell coordinates (decoded from the key; from the lowest-index point when the run holds a point on the
+//     x / y max face, i.e. under hash aliasing), x/y bound filter, final voxel order, and the canvas owner table
+//     (last pillar in voxel order wins a cell, Appendix A.5).
 //
 // export_kernel (optional) dumps the reference-shaped tensors for the parity tests.
 #include "p3p_internal.cuh"
 
 namespace p3p {
+
+// Optional phase timeline (build with -DP3P_TIMELINE): thread 0 of every CTA stamps %globaltimer at the phase
+// boundaries; tools/timeline.py reads them back through p3p_debug_timeline.
+#ifdef P3P_TIMELINE
+__device__ unsigned long long g_timeline[8192][16];
+__device__ __forceinline__ void tl_stamp(int cta, int slot) {
+    if (threadIdx.x == 0 && cta < 8192) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_timeline[cta][slot] = t;
+    }
+}
+#define TL(cta, slot) tl_stamp(cta, slot)
+extern "C" int p3p_debug_timeline(unsigned long long* host, int ctas) {
+    return (int)cudaMemcpyFromSymbol(host, g_timeline, sizeof(unsigned long long) * 16 * (size_t)ctas);
+}
+#else
+#define TL(cta, slot)
+#endif
 
 namespace {
 
@@ -39,6 +63,31 @@ struct ChunkLoc {
     int gstart;   // global index of the tile's chunk 0
     long long p0, p1, tile_start;
 };
+
+// predicated 16-bit shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic, no branches)
+__device__ __forceinline__ unsigned lds_u16(uint32_t addr, int pred) {
+    unsigned v;
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b16 t;\n setp.ne.b32 p, %2, 0;\n mov.b16 t, 0;\n @p ld.shared.u16 t, [%1];\n cvt.u32.u16 %0, t;\n}"
+        : "=r"(v)
+        : "r"(addr), "r"(pred)
+        : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned val, int pred) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b16 t;\n setp.ne.b32 p, %2, 0;\n cvt.u16.u32 t, %1;\n @p st.shared.u16 [%0], t;\n}" ::"r"(addr),
+        "r"(val), "r"(pred)
+        : "memory");
+}
+__device__ __forceinline__ unsigned lds_u32(uint32_t addr, int pred) {
+    unsigned v;
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n mov.b32 %0, 0;\n @p ld.shared.u32 %0, [%1];\n}"
+                 : "=r"(v)
+                 : "r"(addr), "r"(pred)
+                 : "memory");
+    return v;
+}
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v;
@@ -117,38 +166,68 @@ __device__ void write_empty_tile(const GridDev& g, const WsPtrs& ws, int b) {
     if (threadIdx.x == 0) ws.num_pil[b] = 0;
 }
 
-// Per-tile plan, run by the CTA that finished the tile's last chunk.  scratch: >= (2 K + HW) ints of shared memory.
-__device__ void plan_tile(const GridDev& g, const WsPtrs& ws, int b, int* scratch, int* warp_tot) {
+// Per-tile plan, run by the CTA that finished the tile's last chunk.  Keff: keys that can be non-empty (the regular
+// cells only, unless some point of the tile hashed beyond them).  scratch: >= (4 K + HW) ints of shared memory.
+__device__ void plan_tile(const GridDev& g, const WsPtrs& ws, int b, int Keff, int* scratch, int* warp_tot) {
     const int K = g.num_keys, HW = g.ny * g.nx, M = g.M, tid = threadIdx.x;
-    int* tot_s = scratch;       // [K] points per key
-    int* cell_s = tot_s + K;    // [K] packed cell of the run's first point, -1 if dropped
-    int* owner_s = cell_s + K;  // [HW]
+    int* n_s = scratch;         // [K] min(count, M), 0 = empty
+    int* cell_s = n_s + K;      // [K] packed cell of the run, -1 if dropped
+    int* rkey_s = cell_s + K;   // [K] key of pillar r
+    int* rn_s = rkey_s + K;     // [K] n of pillar r
+    int* owner_s = rn_s + K;    // [HW]
     const int* totals = ws.totals + (size_t)b * K;
     const float4* slots = ws.slots + (size_t)b * K * M;
-    // one round trip: counts and rank-0 points of every key, all loads independent (written by other CTAs -> L2 loads)
-    for (int k = tid; k < K; k += kThreads) {
-        const int t = __ldcg(totals + k);
-        const float4 p = __ldcg(slots + (size_t)k * M);
-        int cell = -1;
-        if (t > 0) {
-            int cx, cy, cz;
-            point_cell(g, p.x, p.y, p.z, cx, cy, cz);
-            if (cy < g.nv[1] && cx < g.nv[0]) cell = cx | (cy << 10) | (cz << 20);  // x/y bound filter (A.2)
+    const uint8_t* edge = ws.edge + (size_t)b * K;
+    // counts of every key (written by other CTAs -> L2 loads, 8 independent loads per thread and batch); coordinates
+    // come from the key itself unless the run holds an edge point, in which case its lowest-index kept point decides
+    // (Appendix A.1: hash aliasing)
+    for (int k0 = 0; k0 < Keff; k0 += kThreads * 8) {
+        int t[8];
+        uint8_t e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * kThreads + tid;
+            t[u] = 0; e[u] = 0;
+            if (k < Keff) { t[u] = __ldcg(totals + k); e[u] = __ldcg(edge + k); }
         }
-        tot_s[k] = t;
-        cell_s[k] = cell;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * kThreads + tid;
+            if (k >= Keff) continue;
+            int cell = -1;
+            const int n = t[u] < M ? t[u] : M;
+            if (n > 0) {
+                int cx, cy, cz;
+                if (e[u]) {
+                    float4 best = __ldcg(slots + (size_t)k * M);
+                    for (int i = 1; i < n; ++i) {
+                        const float4 p = __ldcg(slots + (size_t)k * M + i);
+                        if (__float_as_int(p.w) < __float_as_int(best.w)) best = p;
+                    }
+                    point_cell(g, best.x, best.y, best.z, cx, cy, cz);
+                } else {
+                    cz = k / g.stride2;
+                    const int rem = k - cz * g.stride2;
+                    cy = rem / g.stride1;
+                    cx = rem - cy * g.stride1;
+                }
+                if (cy < g.nv[1] && cx < g.nv[0]) cell = cx | (cy << 10) | (cz << 20);  // x/y bound filter (A.2)
+            }
+            n_s[k] = n;
+            cell_s[k] = cell;
+        }
     }
     for (int i = tid; i < HW; i += kThreads) owner_s[i] = -1;
     __syncthreads();
-    const int per = (K + kThreads - 1) / kThreads;
-    const int k0 = tid * per, k1 = (k0 + per < K) ? k0 + per : K;
+    const int per = (Keff + kThreads - 1) / kThreads;
+    const int k0 = tid * per, k1 = (k0 + per < Keff) ? k0 + per : Keff;
     int cnt = 0;
-    for (int k = k0; k < k1; ++k) cnt += (tot_s[k] > 0);
+    for (int k = k0; k < k1; ++k) cnt += (n_s[k] > 0);
     int total_runs;
     int ord = block_exclusive_scan(cnt, warp_tot, &total_runs);
     int cnt2 = 0;
     for (int k = k0; k < k1; ++k) {
-        if (tot_s[k] > 0) {
+        if (n_s[k] > 0) {
             const int r = ord++;
             if (r >= g.Vmax) cell_s[k] = -1;  // only the first max_voxels runs in hash order survive (A.1)
         }
@@ -161,10 +240,12 @@ __device__ void plan_tile(const GridDev& g, const WsPtrs& ws, int b, int* scratc
         if (st < 0) continue;
         const int r = ord2++;
         const size_t pi = (size_t)b * g.Vmax + r;
-        const int t = tot_s[k];
+        const int n = n_s[k];
         ws.pil_key[pi] = k;
-        ws.pil_n[pi] = t < M ? t : M;
+        ws.pil_n[pi] = n;
         ws.pil_coord[pi] = st;
+        rkey_s[r] = k;
+        rn_s[r] = n;
         const int cx = st & 1023, cy = (st >> 10) & 1023;
         atomicMax(&owner_s[cy * g.nx + cx], r);  // scatter collisions: the later row (higher hash) wins (A.5)
     }
@@ -173,29 +254,38 @@ __device__ void plan_tile(const GridDev& g, const WsPtrs& ws, int b, int* scratc
     for (int i = tid; i < HW; i += kThreads) {
         const int o = owner_s[i];
         ws.owner[(size_t)b * HW + i] = o;
-        int d = -1;
-        if (o >= 0) {  // written above by this CTA; visible after the barrier
-            const size_t pi = (size_t)b * g.Vmax + o;
-            d = ws.pil_key[pi] | (ws.pil_n[pi] << 16);
-        }
-        ws.cell_desc[(size_t)b * HW + i] = d;
+        ws.cell_desc[(size_t)b * HW + i] = (o >= 0) ? (rkey_s[o] | (rn_s[o] << 16)) : -1;
     }
 }
 
+// packed per-point word: key (13 bits) | rank inside the warp segment (10 bits) << 13 | retry round (5 bits) << 23
+constexpr int kKeyBits = 13, kOldBits = 10;
+constexpr unsigned kCntMask = (1u << kOldBits) - 1u;
+static_assert(kMaxKeys <= (1 << kKeyBits), "key field too narrow");
+static_assert(kMaxChunkPoints / kWarps <= (1 << (kOldBits - 1)), "segment count field too narrow");
+
 __global__ void __launch_bounds__(kThreads, 3)
 voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __restrict__ offsets, int B, GridDev g, int S,
-                WsPtrs ws, int32_t* __restrict__ point_hash) {
+                WsPtrs ws, int32_t* __restrict__ point_hash, int need_plan) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = g.num_keys;
-    uint16_t* hist = reinterpret_cast<uint16_t*>(smem_raw);  // [kWarps][K]; reused as the plan's scratch
-    unsigned* prefix_s = reinterpret_cast<unsigned*>(smem_raw + (((size_t)kWarps * K * sizeof(uint16_t) + 15) / 16) * 16);  // [Kp]
+    const int Kp = ws.key_stride;  // K rounded up to 8: row stride of chunk_hist (16-byte rows)
+    // [kWarps][K]: walk 1: count (10 bits) | lane tag << 10; afterwards: points of the key in the earlier warps of the CTA
+    uint16_t* hist = reinterpret_cast<uint16_t*>(smem_raw);
+    uint16_t* ctot_s = reinterpret_cast<uint16_t*>(smem_raw + (((size_t)kWarps * K * sizeof(uint16_t) + 15) / 16) * 16);  // [Kp] chunk totals
+    unsigned* prefix_s = reinterpret_cast<unsigned*>(ctot_s + Kp);  // [Kp] points of the key in the earlier chunks of the tile
     __shared__ ChunkLoc loc;
-    __shared__ int s_ticket, s_last;
+    __shared__ int s_ticket, s_last, s_runs[2];
     __shared__ int warp_tot[kWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    TL(blockIdx.x, 0);
     if (tid == 0) s_ticket = (int)atomicAdd(ws.sync, 1u);
-    for (int i = tid; i < kWarps * K; i += kThreads) hist[i] = 0;
+    {
+        uint4* h4 = reinterpret_cast<uint4*>(hist);
+        const int n16 = (kWarps * K * (int)sizeof(uint16_t) + 15) / 16;
+        for (int i = tid; i < n16; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
     const int ticket = s_ticket;
     if (w == 0) locate_chunk(ticket, offsets, B, S, &loc);
@@ -203,130 +293,265 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
     if (ticket < B && offsets[ticket + 1] <= offsets[ticket]) write_empty_tile(g, ws, ticket);
     __syncthreads();
     if (loc.b < 0) return;
+    TL(blockIdx.x, 1);
 
     unsigned* flags = ws.sync + 1;
     unsigned* tile_done = flags + ws.max_chunks;
     const int segS = S / kWarps;  // multiple of 32
     const long long seg0 = loc.p0 + (long long)w * segS;
-    const long long seg1 = (seg0 + segS < loc.p1) ? seg0 + segS : loc.p1;
+    const int seg_n = (int)(((seg0 + segS < loc.p1) ? seg0 + segS : loc.p1) - seg0);  // points of this warp (may be <= 0)
     uint16_t* myhist = hist + (size_t)w * K;
+    uint8_t* edge = ws.edge + (size_t)loc.b * K;
+    const float* seg_pts = pts + seg0 * stride;
 
-    // ---- load: every lane's points into registers, all loads issued before any use ------------------------------
-    float px[kIters], py[kIters], pz[kIters];
-    int key[kIters];
+    // ---- hash + walk 1, software pipelined: the loads of the second half are in flight while the first half is
+    //      counted.  Walk 1 = per-warp histogram of this warp's contiguous segment, 32 consecutive points per step:
+    //      read count, write (count + 1 | lane tag), read back; same-key lanes of a step get one owner per round.
+    int pk[kIters];
+    // bit 0: some key may lie outside the regular cells or be aliased (a point on a max face: z == z_max, y == y_max, ...)
+    // bit 1: some point sits on the x / y max face (its run's coordinates are not decodable from the key)
+    int hi_key = 0;
+    constexpr int kBatch = kIters / 2;
+    const unsigned tag = (unsigned)lane << kOldBits;
+    float px[kBatch], py[kBatch], pz[kBatch];
+    auto load_batch = [&](int j0) {
 #pragma unroll
-    for (int j = 0; j < kIters; ++j) {
-        const long long idx = seg0 + j * 32 + lane;
-        px[j] = 0.f; py[j] = 0.f; pz[j] = 0.f;
-        if (j * 32 < segS && idx < seg1) {
-            const float* p = pts + idx * stride;
-            px[j] = __ldg(p); py[j] = __ldg(p + 1); pz[j] = __ldg(p + 2);
+        for (int jj = 0; jj < kBatch; ++jj) {
+            const int i = (j0 + jj) * 32 + lane;
+            px[jj] = 0.f; py[jj] = 0.f; pz[jj] = 0.f;
+            if (i < seg_n) {
+                const float* p = seg_pts + (size_t)i * stride;
+                px[jj] = __ldg(p); py[jj] = __ldg(p + 1); pz[jj] = __ldg(p + 2);
+            }
         }
-    }
+    };
+    auto hash_batch = [&](int j0) {
 #pragma unroll
-    for (int j = 0; j < kIters; ++j) {
-        const long long idx = seg0 + j * 32 + lane;
-        key[j] = -1;
-        if (j * 32 < segS && idx < seg1) {
-            key[j] = point_key(g, px[j], py[j], pz[j]);
-            if (point_hash) point_hash[idx] = key[j];
+        for (int jj = 0; jj < kBatch; ++jj) {
+            const int j = j0 + jj, i = j * 32 + lane;
+            pk[j] = -1;
+            if (i < seg_n) {
+                bool on_edge;
+                const int k = point_key(g, px[jj], py[jj], pz[jj], on_edge);
+                pk[j] = k;
+                if (on_edge) edge[k] = 1;  // idempotent flag, read by the tile's plan
+                hi_key |= ((k >= g.num_cells) ? 1 : 0) | (on_edge ? 3 : 0);
+                if (point_hash) point_hash[seg0 + i] = k;
+            }
         }
-    }
-    // ---- walk 1: per-warp histogram of this warp's contiguous segment --------------------------------------------
+    };
+    const uint32_t myhist_sa = smem_u32(myhist);
+    auto count_batch = [&](int j0) {
 #pragma unroll
-    for (int j = 0; j < kIters; ++j) {
-        if (j * 32 < segS && seg0 + j * 32 < seg1) {  // warp-uniform
-            const unsigned m = __match_any_sync(0xffffffffu, key[j]);
-            if (key[j] >= 0 && lane == (__ffs(m) - 1)) myhist[key[j]] = (uint16_t)(myhist[key[j]] + __popc(m));
-            __syncwarp();  // the leader lane of a key changes between iterations
+        for (int jj = 0; jj < kBatch; ++jj) {
+            const int j = j0 + jj;
+            if (j * 32 < seg_n) {  // warp-uniform
+                const int k = pk[j];
+                int pend = k >= 0 ? 1 : 0;
+                const uint32_t sa = myhist_sa + 2u * (unsigned)(pend ? k : 0);
+                unsigned myv = 0, myr = 0;
+                for (unsigned round = 0;; ++round) {
+                    const unsigned v = lds_u16(sa, pend) & kCntMask;
+                    const unsigned nv = (v + 1u) | tag;
+                    sts_u16(sa, nv, pend);
+                    __syncwarp();
+                    const int won = pend & (lds_u16(sa, pend) == nv ? 1 : 0);
+                    myv = won ? v : myv;
+                    myr = won ? round : myr;
+                    pend ^= won;
+                    if (!__any_sync(0xffffffffu, pend)) break;
+                }
+                if (k >= 0) pk[j] = k | (int)(myv << kKeyBits) | (int)(myr << (kKeyBits + kOldBits));
+            }
         }
-    }
-    __syncthreads();
-    // ---- publish this chunk's per-key counts, then wait for the earlier chunks of the tile ---------------------
-    const int Kp = ws.key_stride;  // row stride of chunk_hist: K rounded up to 8 (16-byte rows)
+    };
+    load_batch(0);
+    hash_batch(0);
+    load_batch(kBatch);
+    TL(blockIdx.x, 2);
+    count_batch(0);
+    hash_batch(kBatch);
+    count_batch(kBatch);
+    hi_key = (__syncthreads_or(hi_key & 1) ? 1 : 0) | (__syncthreads_or(hi_key & 2) ? 2 : 0);  // (the intrinsic ORs predicates)
+    TL(blockIdx.x, 3);
+    if (tid < 2) s_runs[tid] = 0;
+    // ---- publish this chunk's per-key counts (full rows: zeros beyond the keys in use) ------------------------------
+    const int Kreg = (g.num_cells + 7) / 8 * 8 < Kp ? (g.num_cells + 7) / 8 * 8 : Kp;  // regular cells, 16-byte granular
     {
         uint16_t* dst = ws.chunk_hist + (size_t)ticket * Kp;
-        for (int k = tid; k < K; k += kThreads) {
+        const int Kmine = (hi_key & 1) ? Kp : Kreg;
+        for (int k = tid; k < Kp; k += kThreads) {
             unsigned s = 0;
+            if (k < Kmine && k < K) {
 #pragma unroll
-            for (int ww = 0; ww < kWarps; ++ww) s += hist[(size_t)ww * K + k];
+                for (int ww = 0; ww < kWarps; ++ww) {
+                    const unsigned t = hist[(size_t)ww * K + k] & kCntMask;
+                    hist[(size_t)ww * K + k] = (uint16_t)s;  // points of the key in the earlier warps
+                    s += t;
+                }
+            }
+            ctot_s[k] = (uint16_t)s;
             dst[k] = (uint16_t)s;
         }
         __threadfence();
         __syncthreads();
-        if (tid == 0) st_release(flags + ticket, 1u);
-        for (int cc = tid; cc < loc.c; cc += kThreads)
-            while (ld_acquire(flags + loc.gstart + cc) == 0u) {
+        if (tid == 0) st_release(flags + ticket, 1u | ((unsigned)hi_key << 1));  // bit 0: published
+        TL(blockIdx.x, 4);
+        // wait for the earlier chunks of the tile; learn whether any of them holds keys beyond the regular cells
+        int hi_before = 0;
+        for (int cc = tid; cc < loc.c; cc += kThreads) {
+            unsigned f;
+            while ((f = ld_acquire(flags + loc.gstart + cc)) == 0u) {
             }
-        __syncthreads();
+            hi_before |= (int)(f >> 1);
+        }
+        hi_key |= (__syncthreads_or(hi_before & 1) ? 1 : 0) | (__syncthreads_or(hi_before & 2) ? 2 : 0);
     }
-    // ---- base ranks: earlier chunks of the tile, then earlier warps of this CTA -----------------------------------
+    TL(blockIdx.x, 5);
+    // ---- prefix over the earlier chunks: 8 keys per thread with 16-byte L2 loads, 4 rows in flight per batch -----------
     const int M = g.M;
     const bool last_chunk = (loc.c == loc.nchunks - 1);
-    // sum of the earlier chunks' counts, 8 keys per thread with 16-byte L2 loads, 4 rows in flight per batch
+    const int Kuse = (hi_key & 1) ? Kp : Kreg;  // keys that can be non-empty in this tile so far
+    int open_keys = 0;  // keys of this chunk that still have room (base < M): if none, nothing of the chunk is kept
     for (int k8 = tid; k8 < Kp / 8; k8 += kThreads) {
         unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const uint4* src = reinterpret_cast<const uint4*>(ws.chunk_hist + (size_t)loc.gstart * Kp) + k8;
-        const size_t row = (size_t)Kp / 8;
-        for (int c0 = 0; c0 < loc.c; c0 += 4) {
-            uint4 v[4];
+        if (k8 * 8 < Kuse) {
+            const uint4* src = reinterpret_cast<const uint4*>(ws.chunk_hist + (size_t)loc.gstart * Kp) + k8;
+            const size_t row = (size_t)Kp / 8;
+            for (int c0 = 0; c0 < loc.c; c0 += 4) {
+                uint4 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = (c0 + u < loc.c) ? __ldcg(src + (size_t)(c0 + u) * row) : make_uint4(0, 0, 0, 0);
+                for (int u = 0; u < 4; ++u) v[u] = (c0 + u < loc.c) ? __ldcg(src + (size_t)(c0 + u) * row) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                acc[0] += v[u].x & 0xFFFFu; acc[1] += v[u].x >> 16; acc[2] += v[u].y & 0xFFFFu; acc[3] += v[u].y >> 16;
-                acc[4] += v[u].z & 0xFFFFu; acc[5] += v[u].z >> 16; acc[6] += v[u].w & 0xFFFFu; acc[7] += v[u].w >> 16;
+                for (int u = 0; u < 4; ++u) {
+                    acc[0] += v[u].x & 0xFFFFu; acc[1] += v[u].x >> 16; acc[2] += v[u].y & 0xFFFFu; acc[3] += v[u].y >> 16;
+                    acc[4] += v[u].z & 0xFFFFu; acc[5] += v[u].z >> 16; acc[6] += v[u].w & 0xFFFFu; acc[7] += v[u].w >> 16;
+                }
             }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) prefix_s[k8 * 8 + u] = acc[u];
-    }
-    __syncthreads();
-    for (int k = tid; k < K; k += kThreads) {
-        unsigned run = prefix_s[k];
-#pragma unroll
-        for (int ww = 0; ww < kWarps; ++ww) {
-            const unsigned t = hist[(size_t)ww * K + k];
-            hist[(size_t)ww * K + k] = (uint16_t)(run < (unsigned)M ? run : (unsigned)M);  // saturate: rank >= M is dropped
-            run += t;
+        for (int u = 0; u < 8; ++u) {
+            const int k = k8 * 8 + u;
+            const unsigned own = ctot_s[k];
+            prefix_s[k] = acc[u];
+            open_keys |= (own > 0 && acc[u] < (unsigned)M) ? 1 : 0;
+            if (last_chunk) {
+                const unsigned tot = acc[u] + own;
+                if (k < K) ws.totals[(size_t)loc.b * K + k] = (int)tot;
+                ctot_s[k] = (uint16_t)(tot < (unsigned)M ? tot : (unsigned)M);  // from here on: min(count, M) of the tile
+            }
         }
-        if (last_chunk) ws.totals[(size_t)loc.b * K + k] = (int)run;
     }
-    __syncthreads();
-    // ---- walk 2: stable rank in index order, scatter the survivors ---------------------------------------------------
-    float4* tile_slots = ws.slots + (size_t)loc.b * K * M;
+    open_keys = __syncthreads_or(open_keys);
+    TL(blockIdx.x, 6);
+    // ---- the tile's last chunk knows every count: when no run can be cut, filtered or aliased, the canvas owner table
+    //      follows from the keys directly and the tile needs no plan ------------------------------
+    if (last_chunk) {
+        int direct = 0, hi_ok = 0;
+        if (!need_plan && !(hi_key & 2)) {
+            int r = 0, h = 0;
+            for (int k = tid; k < Kuse && k < K; k += kThreads) {
+                const int nz = ctot_s[k] > 0 ? 1 : 0;
+                if (k < g.num_cells) r += nz; else h += nz;
+            }
+            r = __reduce_add_sync(0xffffffffu, r);
+            h = __reduce_add_sync(0xffffffffu, h);
+            if (lane == 0) { atomicAdd(&s_runs[0], r); atomicAdd(&s_runs[1], h); }
+            __syncthreads();
+            const int R = s_runs[0], H = s_runs[1];
+            // runs are numbered in key order and the first max_voxels survive: regular cells all survive iff R <= Vmax;
+            // the runs beyond them survive all (R + H <= Vmax) or not at all (R == Vmax); anything else needs the plan
+            hi_ok = (R + H <= g.Vmax) ? 1 : 0;
+            direct = (R <= g.Vmax) && (H == 0 || hi_ok || R == g.Vmax);
+        }
+        if (direct) {
+            const int HW = g.ny * g.nx;
+            const int top = hi_ok ? g.ext[2] : g.ext[2] - 1;  // highest z layer whose runs survive
+            for (int cell = tid; cell < HW; cell += kThreads) {
+                const int cy = cell / g.nx, cx = cell - cy * g.nx;
+                int d = -1;
+                if (cx < g.nv[0] && cy < g.nv[1]) {
+                    for (int cz = top; cz >= 0; --cz) {  // the last pillar in voxel order (highest key) owns the cell
+                        const int k = cx + cy * g.stride1 + cz * g.stride2;
+                        const int n = (k < Kuse && k < K) ? (int)ctot_s[k] : 0;
+                        if (n > 0) { d = k | (n << 16); break; }
+                    }
+                }
+                ws.cell_desc[(size_t)loc.b * HW + cell] = d;
+            }
+        }
+        if (tid == 0) ws.tile_hi[loc.b] = (hi_key & 1) | (direct << 1);
+    }
+    // ---- walk 2: rank = earlier chunks + earlier warps + rank in segment; scatter the survivors ---------------------
+    if (open_keys) {
+        // pass A: ranks (registers + shared memory only); pk[j] becomes key | rank << 13 for survivors, -1 otherwise
+        const uint32_t prefix_sa = smem_u32(prefix_s);
 #pragma unroll
-    for (int j = 0; j < kIters; ++j) {
-        if (j * 32 < segS && seg0 + j * 32 < seg1) {  // warp-uniform
-            const int kj = key[j];
-            const unsigned m = __match_any_sync(0xffffffffu, kj);
-            int basecnt = 0;
-            if (kj >= 0) basecnt = myhist[kj];
-            const int rank = basecnt + __popc(m & ((1u << lane) - 1u));
-            if (kj >= 0 && rank < M) {
-                const long long idx = seg0 + j * 32 + lane;
-                tile_slots[(size_t)kj * M + rank] = make_float4(px[j], py[j], pz[j], __int_as_float((int)(idx - loc.tile_start)));
+        for (int j = 0; j < kIters; ++j) {
+            if (j * 32 < seg_n) {  // warp-uniform
+                const int kj = pk[j] < 0 ? -1 : (pk[j] & ((1 << kKeyBits) - 1));
+                const int old = (pk[j] >> kKeyBits) & (int)kCntMask, rnd = (pk[j] >> (kKeyBits + kOldBits)) & 31;
+                const int act = kj >= 0 ? 1 : 0;
+                const unsigned pre = act ? lds_u32(prefix_sa + 4u * (unsigned)kj, act) : (unsigned)M;
+                const unsigned wbase = lds_u16(myhist_sa + 2u * (unsigned)(act ? kj : 0), act);
+                unsigned rank = pre < (unsigned)M ? pre + wbase + (unsigned)old : (unsigned)M;
+                // same-key lanes of a step own their ranks in arbitrary order: re-rank in lane (= index) order in the
+                // one step where the key crosses M
+                const bool crossing = (rank >= (unsigned)M) && (rank < (unsigned)(M + rnd));
+                if (__any_sync(0xffffffffu, crossing)) {
+                    const unsigned m = __match_any_sync(0xffffffffu, kj);
+                    if (pre < (unsigned)M) rank = pre + wbase + (unsigned)(old - rnd) + (unsigned)__popc(m & ((1u << lane) - 1u));
+                }
+                pk[j] = (rank < (unsigned)M) ? (kj | (int)(rank << kKeyBits)) : -1;
+            } else {
+                pk[j] = -1;
             }
-            __syncwarp();
-            if (kj >= 0 && lane == (__ffs(m) - 1)) {
-                const int nb = basecnt + __popc(m);
-                myhist[kj] = (uint16_t)(nb < M ? nb : M);
+        }
+        TL(blockIdx.x, 7);
+        // pass B: survivors re-read their xyz (L1 / L2 hits), all loads of a batch in flight before the first store
+        float4* tile_slots = ws.slots + (size_t)loc.b * K * M;
+#pragma unroll
+        for (int j0 = 0; j0 < kIters; j0 += kBatch) {
+#pragma unroll
+            for (int jj = 0; jj < kBatch; ++jj) {
+                const int i = (j0 + jj) * 32 + lane;
+                if (pk[j0 + jj] >= 0) {
+                    const float* p = seg_pts + (size_t)i * stride;
+                    px[jj] = __ldg(p); py[jj] = __ldg(p + 1); pz[jj] = __ldg(p + 2);
+                }
             }
-            __syncwarp();
+#pragma unroll
+            for (int jj = 0; jj < kBatch; ++jj) {
+                const int j = j0 + jj, i = j * 32 + lane;
+                if (pk[j] >= 0) {
+                    const int kj = pk[j] & ((1 << kKeyBits) - 1), rank = pk[j] >> kKeyBits;
+                    tile_slots[(size_t)kj * M + rank] =
+                        make_float4(px[jj], py[jj], pz[jj], __int_as_float((int)(seg0 + i - loc.tile_start)));
+                }
+            }
         }
     }
     // ---- the last CTA of the tile to get here plans the tile ------------------------------------------------------------
+    TL(blockIdx.x, 8);
     __threadfence();
     __syncthreads();
+    TL(blockIdx.x, 9);
     if (tid == 0) s_last = (atomicAdd(tile_done + loc.b, 1u) == (unsigned)(loc.nchunks - 1)) ? 1 : 0;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    plan_tile(g, ws, loc.b, reinterpret_cast<int*>(smem_raw), warp_tot);
+    TL(blockIdx.x, 10);
+    const int tile_hi = __ldcg(ws.tile_hi + loc.b);
+    if (tile_hi & 2) return;  // owner table already written by the tile's last chunk
+    plan_tile(g, ws, loc.b, (tile_hi & 1) ? K : (g.num_cells < K ? g.num_cells : K), reinterpret_cast<int*>(smem_raw), warp_tot);
+    __syncthreads();
+    TL(blockIdx.x, 11);
 }
 
+// Parity surface (p3p_voxel_outputs): the reference lists a pillar's points by ascending index; slots are unordered.
 __global__ void __launch_bounds__(128)
 export_kernel(GridDev g, int B, WsPtrs ws, p3p_voxel_outputs out) {
+    __shared__ int idx_s[1024];
     const int b = blockIdx.y;
     const int HW = g.ny * g.nx;
     const int np = ws.num_pil[b];
@@ -346,12 +571,21 @@ export_kernel(GridDev g, int B, WsPtrs ws, p3p_voxel_outputs out) {
             if (out.pillar_num_points) out.pillar_num_points[pi] = n;
         }
         const float4* slot = ws.slots + ((size_t)b * g.num_keys + key) * g.M;
+        __syncthreads();
+        for (int s = threadIdx.x; s < n; s += blockDim.x) idx_s[s] = __float_as_int(slot[s].w);
+        __syncthreads();
         for (int s = threadIdx.x; s < g.M; s += blockDim.x) {
+            int pos = s;  // padding rows stay where they are
             float4 p = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-            if (s < n) p = slot[s];
-            if (out.pillar_point_idx) out.pillar_point_idx[pi * g.M + s] = __float_as_int(p.w);
+            if (s < n) {
+                p = slot[s];
+                const int me = idx_s[s];
+                pos = 0;
+                for (int i = 0; i < n; ++i) pos += (idx_s[i] < me) ? 1 : 0;  // indices are distinct
+            }
+            if (out.pillar_point_idx) out.pillar_point_idx[pi * g.M + pos] = __float_as_int(p.w);
             if (out.pillar_points) {
-                float* d = out.pillar_points + (pi * g.M + s) * 3;
+                float* d = out.pillar_points + (pi * g.M + pos) * 3;
                 d[0] = p.x; d[1] = p.y; d[2] = p.z;
             }
         }
@@ -362,13 +596,13 @@ export_kernel(GridDev g, int B, WsPtrs ws, p3p_voxel_outputs out) {
 
 static size_t voxelize_smem_bytes(const GridDev& g) {
     const size_t kp = ((size_t)g.num_keys + 7) / 8 * 8;
-    const size_t hist = ((size_t)kWarps * g.num_keys * sizeof(uint16_t) + 15) / 16 * 16 + kp * sizeof(unsigned);
-    const size_t plan = (size_t)(2 * g.num_keys + g.ny * g.nx) * sizeof(int);
+    const size_t hist = ((size_t)kWarps * g.num_keys * sizeof(uint16_t) + 15) / 16 * 16 + kp * (sizeof(uint16_t) + sizeof(unsigned));
+    const size_t plan = (size_t)(4 * g.num_keys + g.ny * g.nx) * sizeof(int);
     return ((hist > plan ? hist : plan) + 15) / 16 * 16;
 }
 
 int launch_voxelize(const float* pts, int stride, const int64_t* offsets, int B, int64_t total, const GridDev& g,
-                    const WsLayout& l, const WsPtrs& ws, int32_t* point_hash, cudaStream_t st) {
+                    const WsLayout& l, const WsPtrs& ws, int32_t* point_hash, int need_plan, cudaStream_t st) {
     (void)total;
     const size_t smem = voxelize_smem_bytes(g);
     static bool attr_done = false;
@@ -378,7 +612,7 @@ int launch_voxelize(const float* pts, int stride, const int64_t* offsets, int B,
     }
     // ticket counter, chunk flags and per-tile completion counters start at zero for every call
     P3P_CUDA_CHECK(cudaMemsetAsync(ws.sync, 0, l.sync_bytes, st));
-    voxelize_kernel<<<l.max_chunks, kThreads, smem, st>>>(pts, stride, offsets, B, g, l.chunk_points, ws, point_hash);
+    voxelize_kernel<<<l.max_chunks, kThreads, smem, st>>>(pts, stride, offsets, B, g, l.chunk_points, ws, point_hash, need_plan);
     P3P_CUDA_CHECK(cudaGetLastError());
     return P3P_OK;
 }
