@@ -340,9 +340,20 @@ int p3p_profile_end(float* ms_voxelize, float* ms_pfn, int32_t capacity, int32_t
 int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, int32_t height, int32_t width,
                     int32_t patch, const float* weight, const float* bias, int32_t channels, int32_t precision, void* out,
                     int32_t out_dtype, int32_t c_total, int32_t c_offset, void* stream) {
-    (void)images; (void)num_tiles; (void)in_chans; (void)height; (void)width; (void)patch; (void)weight; (void)bias;
-    (void)channels; (void)precision; (void)out; (void)out_dtype; (void)c_total; (void)c_offset; (void)stream;
-    return fail(P3P_ERR_UNSUPPORTED, "placeholder");
+    if (num_tiles < 0) return fail(P3P_ERR_INVALID_ARGUMENT, "num_tiles %d", num_tiles);
+    if (in_chans < 1 || height < 1 || width < 1 || patch < 1 || channels < 1)
+        return fail(P3P_ERR_INVALID_ARGUMENT, "in_chans, height, width, patch and channels must be positive");
+    if (height % patch != 0 || width % patch != 0)
+        return fail(P3P_ERR_INVALID_ARGUMENT, "image %d x %d is not a whole number of %d-px patches", height, width, patch);
+    if (precision < P3P_PRECISION_FP32 || precision > P3P_PRECISION_BF16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+    if (out_dtype != P3P_DTYPE_F32 && out_dtype != P3P_DTYPE_BF16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown dtype %d", out_dtype);
+    if (c_offset < 0 || c_offset + channels > c_total)
+        return fail(P3P_ERR_INVALID_ARGUMENT, "channels [%d, %d) outside c_total %d", c_offset, c_offset + channels, c_total);
+    if (num_tiles == 0) return P3P_OK;
+    if (!images || !weight || !out) return fail(P3P_ERR_INVALID_ARGUMENT, "null images, weight or out");
+    if (!aligned16(images) || !aligned16(weight) || !aligned16(out)) return fail(P3P_ERR_INVALID_ARGUMENT, "misaligned pointer");
+    return launch_patch_embed(images, num_tiles, in_chans, height, width, patch, weight, bias, channels, precision, out, out_dtype,
+                              c_total, c_offset, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

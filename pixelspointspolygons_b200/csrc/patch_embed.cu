@@ -1,11 +1,276 @@
 // patch_embed.cu -- image patch embedding written into the early-fusion concat buffer (sm_100a).
+//
+// Replaces `x_image = self.image_embed(x_image)` of the fusion encoders
+// (R:pixelspointspolygons/models/fusion_layers/early_fusion_vit.py:69-70,99 and early_fusion_vit_cnn.py:67-68,90;
+// timm PatchEmbed with flatten=False: Conv2d(in_chans, C, kernel=P, stride=P, bias), output NCHW)
+// and the image half of `torch.cat((x_image, x_lidar), dim=1)` (early_fusion_vit.py:121, row a11): the result goes
+// straight to channels [c_offset, c_offset + C) of the (B, c_total, H/P, W/P) buffer, so the concat copy never runs.
+//
+// A stride-P PxP convolution is one GEMM per tile, out[ch][cell] = sum_k W[ch][k] X[k][cell] + bias[ch] with
+// k = (c, py, px) -- the natural memory order of the (C, in_chans, P, P) weight -- and X[k][cell] the pixel
+// (c, cy*P + py, cx*P + px).  With P = 8 one (c, py) row of a patch is 8 consecutive fp32 pixels = 32 bytes = exactly
+// one UMMA K step (8 tf32 / 16 bf16 -> 32 bytes), so the im2col matrix is never built: every 32-byte pixel run is
+// copied (coalesced along the image row) to its place in the swizzled K-major B operand in shared memory.
+//
+// patch_embed_tc_kernel: CTA = (row group of R cell rows, 128-channel tile, image).  D[128 ch x R*nx cells] lives in
+//   TMEM; tcgen05.mma kind::tf32 (fp32 contract) or kind::f16 on bf16 operands (bf16 contract), fp32 accumulate;
+//   epilogue: tcgen05.ld, + bias, NCHW rows of R*nx contiguous values per channel.
+// patch_embed_simt_kernel: exact fp32 FMA for any P / shape -- the GPU-side cross-check and the fp32 route.
 #include "p3p_internal.cuh"
 
 namespace p3p {
+namespace {
 
-int launch_patch_embed(const float*, int, int, int, int, int, const float*, const float*, int, int, void*, int, int, int,
-                       cudaStream_t) {
-    return fail(P3P_ERR_UNSUPPORTED, "patch embed kernel not built yet");
+__device__ __forceinline__ void store_out(void* out, int out_dtype, int64_t idx, float v) {
+    if (out_dtype == P3P_DTYPE_F32)
+        static_cast<float*>(out)[idx] = v;
+    else
+        static_cast<unsigned short*>(out)[idx] = (unsigned short)(pack_bf16(v, 0.f) & 0xFFFF);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact fp32 kernel: one CTA per (cell, image); the patch sits in shared memory, one thread per channel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+patch_embed_simt_kernel(const float* __restrict__ img, int in_chans, int H, int W, int P, const float* __restrict__ weight,
+                        const float* __restrict__ bias, int C, void* out, int out_dtype, int c_total, int c_offset) {
+    extern __shared__ float patch[];  // [in_chans * P * P]
+    const int nx = W / P, ny = H / P;
+    const int cell = blockIdx.x, b = blockIdx.y;
+    const int cy = cell / nx, cx = cell - cy * nx;
+    const int K = in_chans * P * P;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int c = k / (P * P), r = k - c * P * P, py = r / P, px = r - py * P;
+        patch[k] = img[(((int64_t)b * in_chans + c) * H + cy * P + py) * W + cx * P + px];
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+        const float* w = weight + (int64_t)ch * K;
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc = __fmaf_rn(w[k], patch[k], acc);
+        if (bias) acc += bias[ch];
+        store_out(out, out_dtype, ((int64_t)b * c_total + c_offset + ch) * (ny * nx) + cell, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core kernel (P == 8)
+// ------------------------------------------------------------------------------------------------
+constexpr int kPeThreads = 256;
+
+struct PeArgs {
+    const float* img;
+    const float* weight;
+    const float* bias;
+    void* out;
+    int in_chans, H, W, C, nx, ny;
+    int rows;       // cell rows per CTA
+    int N;          // rows * nx: MMA N (multiple of 16, <= 128)
+    int out_dtype, c_total, c_offset;
+};
+
+// Operand rows are K-major and split into 128-byte chunks (SWIZZLE_128B atoms, 8 rows x 128 B); chunk q of a tile
+// with `nrows` rows starts at q * nrows * 128.  One 32-byte pixel run (c, py) of 8 fp32 values becomes
+//   tf32: 2 x 16-byte units  (chunk = k8 / 4, units (k8 % 4) * 2 + {0, 1}),   k8 = c * 8 + py
+//   bf16: 1 x 16-byte unit   (chunk = k8 / 8, unit k8 % 8)
+template <bool kTf32>
+__device__ __forceinline__ void put_run(unsigned char* tile, int nrows, int row, int k8, const float4& lo, const float4& hi) {
+    if constexpr (kTf32) {
+        unsigned char* base = tile + (size_t)(k8 >> 2) * nrows * 128 + (size_t)row * 128;
+        const int u = (k8 & 3) * 2;
+        const uint4 a = make_uint4(to_tf32(lo.x), to_tf32(lo.y), to_tf32(lo.z), to_tf32(lo.w));
+        const uint4 b = make_uint4(to_tf32(hi.x), to_tf32(hi.y), to_tf32(hi.z), to_tf32(hi.w));
+        *reinterpret_cast<uint4*>(base + (((u + 0) ^ (row & 7)) * 16)) = a;
+        *reinterpret_cast<uint4*>(base + (((u + 1) ^ (row & 7)) * 16)) = b;
+    } else {
+        unsigned char* base = tile + (size_t)(k8 >> 3) * nrows * 128 + (size_t)row * 128;
+        const int u = k8 & 7;
+        const uint4 a = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+        *reinterpret_cast<uint4*>(base + ((u ^ (row & 7)) * 16)) = a;
+    }
+}
+
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <bool kTf32>
+__global__ void __launch_bounds__(kPeThreads, 1) patch_embed_tc_kernel(PeArgs a) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t raw = smem_u32(smem_dyn);
+    unsigned char* base = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
+    const int K8 = a.in_chans * 8;                    // 32-byte pixel runs per operand row
+    const int NQ = kTf32 ? K8 / 4 : K8 / 8;           // 128-byte chunks per operand row
+    const int Npad = (a.N + 7) / 8 * 8;               // (N is a multiple of 16 already)
+    unsigned char* sA = base;                         // [NQ][128 rows][128 B]
+    unsigned char* sB = sA + (size_t)NQ * 128 * 128;  // [NQ][Npad rows][128 B]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rg = blockIdx.x, mt = blockIdx.y, b = blockIdx.z;
+    const int cy0 = rg * a.rows;
+
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    if (tid == 32) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    // ---- A: 128 channels x K weights, natural (C, in_chans, 8, 8) order == K-major rows; B: the pixel runs of `rows`
+    //      cell rows: image rows (c, cy0*8 + y), nx runs each.  kDepth runs (2 x float4 each) per thread in flight. ------
+    {
+        constexpr int kDepth = 6;
+        const int runs_a = 128 * K8;
+        const int img_rows = a.in_chans * a.rows * 8;
+        const int runs_b = img_rows * a.nx;
+        const int runs = runs_a + runs_b;
+        const float* src_b = a.img + (size_t)b * a.in_chans * a.H * a.W;
+        for (int i0 = tid; i0 < runs; i0 += kPeThreads * kDepth) {
+            float4 lo[kDepth], hi[kDepth];
+            int row[kDepth], k8v[kDepth];
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const int i = i0 + d * kPeThreads;
+                lo[d] = make_float4(0.f, 0.f, 0.f, 0.f); hi[d] = lo[d];
+                row[d] = -1; k8v[d] = 0;
+                if (i < runs_a) {
+                    const int r = i / K8, k8 = i - r * K8;
+                    const int ch = mt * 128 + r;
+                    row[d] = r; k8v[d] = k8;
+                    if (ch < a.C) {
+                        const float4* src = reinterpret_cast<const float4*>(a.weight + ((size_t)ch * K8 + k8) * 8);
+                        lo[d] = __ldg(src);
+                        hi[d] = __ldg(src + 1);
+                    }
+                } else if (i < runs) {
+                    const int ib = i - runs_a;
+                    const int ir = ib / a.nx, cx = ib - ir * a.nx;
+                    const int c = ir / (a.rows * 8), yl = ir - c * (a.rows * 8);
+                    const int cyl = yl >> 3, py = yl & 7;
+                    const float4* src = reinterpret_cast<const float4*>(src_b + ((size_t)c * a.H + cy0 * 8 + yl) * a.W + cx * 8);
+                    lo[d] = __ldg(src);
+                    hi[d] = __ldg(src + 1);
+                    row[d] = 128 + cyl * a.nx + cx; k8v[d] = c * 8 + py;
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                if (row[d] < 0) continue;
+                if (row[d] < 128)
+                    put_run<kTf32>(sA, 128, row[d], k8v[d], lo[d], hi[d]);
+                else
+                    put_run<kTf32>(sB, Npad, row[d] - 128, k8v[d], lo[d], hi[d]);
+            }
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc(kTf32, 128, a.N);
+            const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, SWIZZLE_128B
+            const uint32_t a_lo = (smem_u32(sA) >> 4) | (1u << 16), b_lo = (smem_u32(sB) >> 4) | (1u << 16);
+            for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const uint32_t ao = (uint32_t)((q * 128 * 128 + s * 32) >> 4), bo = (uint32_t)((q * Npad * 128 + s * 32) >> 4);
+                    tc_mma<kTf32>(tmem_base, ((uint64_t)desc_hi << 32) | (a_lo + ao), ((uint64_t)desc_hi << 32) | (b_lo + bo), idesc,
+                                  (q | s) != 0);
+                }
+            }
+            tc_commit(&bar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    // ---- epilogue: thread = channel (TMEM lane), warps 0-3 take the first 16-column blocks, warps 4-7 the rest ----------
+    {
+        const int quad = warp & 3, hi_half = warp >> 2;
+        const int ch = mt * 128 + quad * 32 + lane;
+        const int nblk = a.N / 16, split = (nblk + 1) / 2;
+        const int blk0 = hi_half ? split : 0, blk1 = hi_half ? nblk : split;
+        const float bv = (a.bias && ch < a.C) ? a.bias[ch] : 0.f;
+        const int64_t row0 = ((int64_t)b * a.c_total + a.c_offset + ch) * ((int64_t)a.ny * a.nx) + (int64_t)cy0 * a.nx;
+        for (int blk = blk0; blk < blk1; ++blk) {
+            float v[16];
+            tmem_ld16_wait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(blk * 16), v);
+            if (ch < a.C) {
+                if (a.out_dtype == P3P_DTYPE_F32) {
+                    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(a.out) + row0 + blk * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i] + bv, v[4 * i + 1] + bv, v[4 * i + 2] + bv, v[4 * i + 3] + bv);
+                } else {
+                    uint4* dst = reinterpret_cast<uint4*>(static_cast<unsigned short*>(a.out) + row0 + blk * 16);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        dst[i] = make_uint4(pack_bf16(v[8 * i] + bv, v[8 * i + 1] + bv), pack_bf16(v[8 * i + 2] + bv, v[8 * i + 3] + bv),
+                                            pack_bf16(v[8 * i + 4] + bv, v[8 * i + 5] + bv), pack_bf16(v[8 * i + 6] + bv, v[8 * i + 7] + bv));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+
+int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, int P, const float* weight, const float* bias,
+                       int C, int precision, void* out, int out_dtype, int c_total, int c_offset, cudaStream_t st) {
+    if (B <= 0) return P3P_OK;
+    const int nx = W / P, ny = H / P;
+    const bool tf32 = (precision != P3P_PRECISION_BF16);
+    // tensor-core route: 8x8 patches; a row group of `rows` cell rows with rows * nx a multiple of 16 and <= 128 that
+    // divides ny; operands (128 + N rows of K values) within the shared-memory budget; 16-byte aligned output rows
+    int rows = 0;
+    if (precision != P3P_PRECISION_FP32 && P == 8 && (W % 8) == 0) {
+        for (int r = ny; r >= 1; --r) {
+            const int n = r * nx;
+            if (ny % r == 0 && n <= 128 && n % 16 == 0) { rows = r; break; }
+        }
+    }
+    const size_t esize = tf32 ? 4 : 2;
+    const size_t K = (size_t)in_chans * 64;
+    const size_t smem = 1024 + (128 + (size_t)rows * nx) * K * esize;
+    const bool k_ok = tf32 ? (K % 32 == 0) : (K % 64 == 0);
+    if (rows > 0 && k_ok && smem <= 200 * 1024 && ((size_t)ny * nx * (out_dtype == P3P_DTYPE_F32 ? 4 : 2)) % 16 == 0) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_done = true;
+        }
+        PeArgs a;
+        a.img = images; a.weight = weight; a.bias = bias; a.out = out;
+        a.in_chans = in_chans; a.H = H; a.W = W; a.C = C; a.nx = nx; a.ny = ny;
+        a.rows = rows; a.N = rows * nx;
+        a.out_dtype = out_dtype; a.c_total = c_total; a.c_offset = c_offset;
+        dim3 grid((unsigned)(ny / rows), (unsigned)((C + 127) / 128), (unsigned)B);
+        if (tf32)
+            patch_embed_tc_kernel<true><<<grid, kPeThreads, smem, st>>>(a);
+        else
+            patch_embed_tc_kernel<false><<<grid, kPeThreads, smem, st>>>(a);
+        P3P_CUDA_CHECK(cudaGetLastError());
+        return P3P_OK;
+    }
+    const size_t smem_simt = (size_t)in_chans * P * P * sizeof(float);
+    if (smem_simt > 48 * 1024) return fail(P3P_ERR_UNSUPPORTED, "patch of %d x %d x %d values exceeds the shared-memory budget", in_chans, P, P);
+    dim3 grid((unsigned)(ny * nx), (unsigned)B);
+    patch_embed_simt_kernel<<<grid, 128, smem_simt, st>>>(images, in_chans, H, W, P, weight, bias, C, out, out_dtype, c_total, c_offset);
+    P3P_CUDA_CHECK(cudaGetLastError());
+    return P3P_OK;
 }
 
 }  // namespace p3p

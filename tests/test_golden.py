@@ -1,0 +1,106 @@
+"""Committed golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the oracle).
+
+CPU: the oracle still reproduces them (pins oracle/ against drift).  GPU (-m gpu): the CUDA path, through the C ABI,
+reproduces them -- integer outputs bit exact, features within the fp32-contract tolerance 1e-3 of scale."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pillars_oracle as po
+from pixelspointspolygons_b200 import PointPillarsEncoder, default_cfg
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LIDAR = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "*.npz")) if "patch_embed" not in p)
+TOL = 1e-3
+
+
+def load(name):
+    z = np.load(os.path.join(HERE, name + ".npz"))
+    tiles = [z["points"][a:b] for a, b in zip(z["offsets"][:-1], z["offsets"][1:])]
+    grid = po.GridSpec(max_num_points=int(z["grid_max_num_points"]), max_voxels=tuple(int(v) for v in z["grid_max_voxels"]),
+                       drop_overflow=bool(z["grid_drop_overflow"]), feat_channels=(64, int(z["channels"])))
+    sd, _ = po.synth_weights(int(z["weight_seed"]), feat_channels=(64, int(z["channels"])))
+    return z, tiles, grid, sd
+
+
+def test_fixture_set_is_complete():
+    assert LIDAR == ["edge_alias_z100", "edge_occupancy_M", "edge_vmax_cut", "ragged_small"]
+    assert os.path.isfile(os.path.join(HERE, "patch_embed.npz")) and os.path.isfile(os.path.join(HERE, "make_golden.py"))
+
+
+@pytest.mark.parametrize("name", LIDAR)
+def test_oracle_reproduces_golden(name):
+    z, tiles, grid, sd = load(name)
+    enc = po.OraclePointPillarsEncoder(grid).eval()
+    enc.load_state_dict(sd)
+    with torch.no_grad():
+        voxels, nums, coors, dense = enc.voxelize(tiles)
+        feats, _, _ = enc.pillar_features(tiles)
+        canvas = enc(tiles, return_flattened=False)
+    assert np.array_equal(coors.numpy(), z["coors"]) and np.array_equal(nums.numpy(), z["num_points"])
+    assert np.array_equal(dense.numpy(), z["dense_idx"])
+    assert np.allclose(feats.numpy(), z["pillar_features"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(canvas.double().sum(dim=(2, 3)).numpy(), z["canvas_checksum"], rtol=1e-5, atol=1e-4)
+    # the numpy restatement agrees with the stored hashes too
+    h = np.concatenate([po.voxelize_numpy(t, grid, 1)["point_hash"] for t in tiles]) if len(z["points"]) else np.zeros(0)
+    assert np.array_equal(h, z["point_hash"])
+
+
+def test_oracle_patch_embed_reproduces_golden():
+    z = np.load(os.path.join(HERE, "patch_embed.npz"))
+    C = int(z["channels"])
+    img = torch.rand(1, 3, 224, 224, generator=torch.Generator().manual_seed(int(z["image_seed"])))
+    pe = po.OraclePatchEmbed(embed_dim=C).eval()
+    pe.load_state_dict(po.synth_weights(int(z["weight_seed"]), feat_channels=(64, C))[1])
+    with torch.no_grad():
+        assert np.allclose(pe(img).numpy(), z["out"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", LIDAR)
+def test_cuda_path_reproduces_golden(cuda_device, name):
+    z, tiles, grid, sd = load(name)
+    C = int(z["channels"])
+    cfg = default_cfg(device=str(cuda_device), max_num_points_per_voxel=grid.max_num_points, max_num_voxels=grid.max_voxels,
+                      patch_feature_dim=C, p3p_drop_overflow=grid.drop_overflow)
+    enc = PointPillarsEncoder(cfg, voxel_encoder={"in_channels": 3, "feat_channels": [64, C]},
+                              scatter={"in_channels": C, "output_shape": [28, 28]}).to(cuda_device).eval()
+    enc.load_state_dict(sd)
+    x = torch.nested.nested_tensor_from_jagged(torch.from_numpy(z["points"]).to(cuda_device), torch.from_numpy(z["offsets"]).to(cuda_device))
+    raw = enc.voxelize_raw(x)
+    assert np.array_equal(raw["point_hash"].cpu().numpy(), z["point_hash"])
+    V = raw["pillar_coords"].shape[1]
+    mask = (torch.arange(V).view(1, -1) < raw["num_pillars"].cpu().view(-1, 1))
+    assert np.array_equal(raw["pillar_coords"].cpu()[mask].numpy(), z["coors"])
+    assert np.array_equal(raw["pillar_num_points"].cpu()[mask].numpy(), z["num_points"])
+    assert np.array_equal(raw["pillar_point_idx"].cpu()[mask].numpy(), z["dense_idx"])
+    for prec in ("fp32", "tf32"):
+        feats, coors = enc.pillar_features(x, precision=prec)
+        scale = max(float(np.abs(z["pillar_features"]).max()), 1e-6) if z["pillar_features"].size else 1.0
+        assert np.abs(feats.cpu().numpy() - z["pillar_features"]).max(initial=0.0) <= TOL * scale, (name, prec)
+        enc.precision = prec
+        with torch.no_grad():
+            canvas = enc(x, return_flattened=False)
+        nz = np.argwhere((canvas != 0).any(1).cpu().numpy()).astype(np.int32)
+        assert np.array_equal(nz, z["canvas_nonzero_cells"])
+        cs = canvas.double().sum(dim=(2, 3)).cpu().numpy()
+        assert np.abs(cs - z["canvas_checksum"]).max() <= TOL * scale * max(1, len(z["canvas_nonzero_cells"]))
+
+
+@pytest.mark.gpu
+def test_cuda_patch_embed_reproduces_golden(cuda_device):
+    from pixelspointspolygons_b200 import PatchEmbed
+
+    z = np.load(os.path.join(HERE, "patch_embed.npz"))
+    C = int(z["channels"])
+    img = torch.rand(1, 3, 224, 224, generator=torch.Generator().manual_seed(int(z["image_seed"])))
+    pe = PatchEmbed(224, 8, 3, C).to(cuda_device).eval()
+    pe.load_state_dict(po.synth_weights(int(z["weight_seed"]), feat_channels=(64, C))[1])
+    scale = float(np.abs(z["out"]).max())
+    for prec, tol in (("fp32", 1e-5), ("tf32", 1e-3), ("bf16", 1e-2)):
+        pe.precision = prec
+        out = pe(img.to(cuda_device)).cpu().numpy()
+        assert np.abs(out - z["out"]).max() <= tol * scale, prec

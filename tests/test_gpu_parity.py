@@ -210,3 +210,95 @@ def test_training_path_runs_and_matches_train_mode_oracle(cuda_device):
     out.sum().backward()
     assert enc.voxel_encoder.pfn_layers[1].linear.weight.grad is not None
     assert torch.allclose(enc.voxel_encoder.pfn_layers[0].norm.running_mean.cpu(), ref.voxel_encoder.pfn_layers[0].norm.running_mean, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# image patch embedding + early-fusion concat
+# ---------------------------------------------------------------------------------------------------------------
+def build_fusion(dev, seed=0, lidar_dropout=None, precision="tf32"):
+    from pixelspointspolygons_b200.fusion import EarlyFusionFrontEnd
+
+    cfg = default_cfg(device=str(dev), lidar_dropout=lidar_dropout, p3p_precision=precision)
+    fe = EarlyFusionFrontEnd(cfg).to(dev).eval()
+    sd, sdi = po.synth_weights(seed)
+    fe.lidar_embed.load_state_dict(sd)
+    fe.image_embed.load_state_dict(sdi)
+    ref_l = po.OraclePointPillarsEncoder(po.GridSpec()).eval()
+    ref_l.load_state_dict(sd)
+    ref_i = po.OraclePatchEmbed().eval()
+    ref_i.load_state_dict(sdi)
+    return fe, ref_i, ref_l
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+def test_patch_embed_matches_conv2d(cuda_device, prec):
+    fe, ref_i, _ = build_fusion(cuda_device, seed=12, precision=prec)
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(3, 3, 224, 224, generator=g)
+    img[1] = (img[1] - 0.5) * 4.0  # normalised images are not confined to [0, 1]
+    with torch.no_grad():
+        r = ref_i(img)
+    fe.image_embed.precision = prec
+    out = fe.image_embed(img.to(cuda_device))
+    assert out.shape == (3, 384, 28, 28)
+    assert_close(out, r, TOL[prec], f"patch embed {prec}")
+    # bf16 output buffer, channel offset inside a wider buffer
+    buf = torch.full((3, 768, 28, 28), 3.0, dtype=torch.bfloat16, device=cuda_device)
+    fe.image_embed.forward_into(img.to(cuda_device), buf, 768, 0, precision=prec)
+    assert torch.all(buf[:, 384:] == 3.0)
+    assert_close(buf[:, :384], r, max(TOL[prec], 8e-3), f"patch embed {prec} bf16 out")
+
+
+def test_patch_embed_other_shapes_take_the_exact_route(cuda_device):
+    from pixelspointspolygons_b200.fusion import PatchEmbed
+
+    g = torch.Generator().manual_seed(6)
+    for (size, patch, chans, dim) in [(64, 16, 3, 96), (48, 4, 1, 40), (224, 8, 3, 200), (128, 8, 3, 384)]:
+        pe = PatchEmbed(size, patch, chans, dim).to(cuda_device).eval()
+        ref = torch.nn.Conv2d(chans, dim, patch, patch)
+        with torch.no_grad():
+            ref.weight.copy_(torch.randn(ref.weight.shape, generator=g) * 0.1)
+            ref.bias.copy_(torch.randn(dim, generator=g) * 0.1)
+        pe.proj.load_state_dict(ref.state_dict())
+        img = torch.rand(2, chans, size, size, generator=g)
+        with torch.no_grad():
+            r = ref(img)
+        assert_close(pe(img.to(cuda_device)), r, 1e-3, f"patch embed {size}/{patch}/{chans}/{dim}")
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_early_fusion_concat_matches_oracle(cuda_device, prec):
+    fe, ref_i, ref_l = build_fusion(cuda_device, seed=13, precision=prec)
+    tiles = [po.synth_tile(20000, 41), po.synth_tile(500, 42, clustered=True), np.zeros((0, 3), np.float32)]
+    img = torch.rand(3, 3, 224, 224, generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        r = po.early_fusion_front(ref_i, ref_l, img, tiles)
+        rz = po.early_fusion_front(ref_i, ref_l, img, tiles, apply_lidar_dropout=True)
+        out = fe(img.to(cuda_device), to_nested(tiles, cuda_device))
+    assert out.shape == (3, 768, 28, 28)
+    assert_close(out[:, :384], r[:, :384], TOL[prec], "image half")
+    assert_close(out[:, 384:], r[:, 384:], TOL[prec], "lidar half")
+    # LiDAR dropout with p = 1.0 (what the trainer forces during validation): x_lidar * 0.0
+    fe.cfg.experiment.lidar_dropout = 1.0
+    with torch.no_grad():
+        z = fe(img.to(cuda_device), to_nested(tiles, cuda_device))
+    assert torch.all(z[:, 384:] == 0)
+    assert_close(z[:, :384], rz[:, :384], TOL[prec], "image half under dropout")
+    fe.cfg.experiment.lidar_dropout = 0.0  # rand <= 0.0 practically never: LiDAR half present
+    with torch.no_grad():
+        k = fe(img.to(cuda_device), to_nested(tiles, cuda_device))
+    assert torch.equal(k, out)
+
+
+def test_sharded_batch_equals_single_gpu_batch(cuda_device):
+    """encoding the shards of a batch one by one == encoding the whole batch (bit identical)."""
+    from pixelspointspolygons_b200 import shard
+
+    enc, _ = build(cuda_device, po.GridSpec(), seed=14)
+    tiles = [po.synth_tile(3000 + 997 * i, 50 + i, clustered=(i % 3 == 0)) for i in range(11)]
+    x = to_nested(tiles, cuda_device)
+    with torch.no_grad():
+        whole = enc(x, return_flattened=False)
+        for world in (2, 4, 8):
+            parts = [enc(shard.shard_lidar(x, r, world), return_flattened=False) for r in range(world)]
+            assert torch.equal(torch.cat(parts, 0), whole), world
