@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--workload", default="lidar", choices=["lidar", "fusion"])
     ap.add_argument("--batch", type=int, default=16, help="tiles per GPU per step")
     ap.add_argument("--points", type=int, default=100_000, help="points per tile")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "tf32", "fp16", "bf16"])
     ap.add_argument("--max-points-per-voxel", type=int, default=64)
     ap.add_argument("--sets", type=int, default=8, help="rotating input/output sets (must exceed L2 in total)")
     ap.add_argument("--no-graph", action="store_true", help="launch through the C ABI every step instead of CUDA graphs")
@@ -351,7 +351,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     which = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
-    tensor_peak = bf16_peak if args.precision == "bf16" else bf16_peak / 2.0  # tf32 dense = half the bf16 rate
+    tensor_peak = bf16_peak if args.precision in ("bf16", "fp16") else bf16_peak / 2.0  # tf32 dense = half the 16-bit rate
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "pfn_traffic.json"))).get(args.precision)
@@ -362,7 +362,7 @@ def main():
     roofline = {"kernel": "pfn_tc_kernel" if (args.precision != "fp32" and M == 64) else "pfn_simt_kernel",
                 "bound": "tensor", "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": (achieved_tf / tensor_peak) if achieved_tf else None, "traffic": traffic,
-                "peak_source": which + ("; tf32 peak taken as bf16/2" if args.precision != "bf16" else ""),
+                "peak_source": which + ("; tf32 peak taken as bf16/2" if args.precision not in ("bf16", "fp16") else ""),
                 "flops_per_launch": flops, "ms_per_launch": stage_ms["pfn"], "kept_points": kept, "pillars": pillars}
     bytes_tile = algorithmic_bytes_per_tile(N, args.workload)
     per_gpu_gbs = bytes_tile * (value / world) / 1e9
@@ -391,7 +391,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16", "fp16": "f16 operands, f32 accumulate, f32 in/out"}[args.precision], "data": "synthetic",
             "config": workload_config(args), "mpoints_per_s": value * N / 1e6,
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launch_mode": "cuda_graph" if graphs else "c_abi_per_step",
             "roofline": roofline, "hbm_roofline": hbm, "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "clocks": clocks,

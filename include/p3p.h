@@ -54,7 +54,11 @@ enum {
 enum {
     P3P_PRECISION_FP32 = 0, /* exact fp32 FMA on CUDA cores (any M; slow; GPU-side cross-check) */
     P3P_PRECISION_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate -- the fp32 (1e-3) contract */
-    P3P_PRECISION_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate -- the bf16 (1e-2) contract */
+    P3P_PRECISION_BF16 = 2, /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate -- the bf16 (1e-2) contract */
+    P3P_PRECISION_FP16 = 3  /* tcgen05 kind::f16 (fp16 operands: 10 mantissa bits like tf32, half the operand bytes), fp32
+                               accumulate -- meets the fp32 (1e-3) contract while the layer-0 activations and the folded
+                               weights stay inside the fp16 range (|v| < 65504); the caller checks that (the Python
+                               module bounds it from the weights and the grid extent and falls back to TF32) */
 };
 
 /* Output tensor layouts of p3p_encode. */

@@ -7,7 +7,7 @@ import os
 
 from .build import LIB_PATH
 
-P3P_PRECISION = {"fp32": 0, "tf32": 1, "bf16": 2}
+P3P_PRECISION = {"fp32": 0, "tf32": 1, "bf16": 2, "fp16": 3}
 P3P_LAYOUT_NCHW, P3P_LAYOUT_NLC = 0, 1
 P3P_DTYPE_F32, P3P_DTYPE_BF16 = 0, 1
 P3P_GRID_DROP_OVERFLOW = 1

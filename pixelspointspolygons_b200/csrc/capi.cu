@@ -148,7 +148,7 @@ static int check_blob(int C, BlobLayout* bl) {
 
 static int run_pfn(const PfnArgs& a, int precision, cudaStream_t st) {
     if (precision == P3P_PRECISION_FP32) return launch_pfn_simt(a, st);
-    if (precision != P3P_PRECISION_TF32 && precision != P3P_PRECISION_BF16)
+    if (precision != P3P_PRECISION_TF32 && precision != P3P_PRECISION_BF16 && precision != P3P_PRECISION_FP16)
         return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
     // The tensor-core kernel covers the shipped encoder configs (M = 64, C <= 384); other shapes of the density
     // ablation take the exact-fp32 kernel, which is at least as accurate as either tensor-core contract.
@@ -184,7 +184,7 @@ int p3p_pfn_prepare(const p3p_pfn_params* p, int32_t precision, void* blob, size
     if (!p->linear0_weight || !p->norm0_weight || !p->norm0_bias || !p->norm0_mean || !p->norm0_var ||
         !p->linear1_weight || !p->norm1_weight || !p->norm1_bias || !p->norm1_mean || !p->norm1_var)
         return fail(P3P_ERR_INVALID_ARGUMENT, "null weight pointer");
-    if (precision < P3P_PRECISION_FP32 || precision > P3P_PRECISION_BF16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+    if (precision < P3P_PRECISION_FP32 || precision > P3P_PRECISION_FP16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
     BlobLayout bl;
     int rc = check_blob(p->channels, &bl);
     if (rc) return rc;
@@ -345,7 +345,7 @@ int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, in
         return fail(P3P_ERR_INVALID_ARGUMENT, "in_chans, height, width, patch and channels must be positive");
     if (height % patch != 0 || width % patch != 0)
         return fail(P3P_ERR_INVALID_ARGUMENT, "image %d x %d is not a whole number of %d-px patches", height, width, patch);
-    if (precision < P3P_PRECISION_FP32 || precision > P3P_PRECISION_BF16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+    if (precision < P3P_PRECISION_FP32 || precision > P3P_PRECISION_FP16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
     if (out_dtype != P3P_DTYPE_F32 && out_dtype != P3P_DTYPE_BF16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown dtype %d", out_dtype);
     if (c_offset < 0 || c_offset + channels > c_total)
         return fail(P3P_ERR_INVALID_ARGUMENT, "channels [%d, %d) outside c_total %d", c_offset, c_offset + channels, c_total);

@@ -209,8 +209,8 @@ __device__ __forceinline__ Item fetch_item(const PfnArgs& a, int64_t item) {
     Item it;
     it.valid = 0; it.n = 0; it.key = 0; it.ctr_x = 0.f; it.ctr_y = 0.f; it.cell = 0; it.b = 0;
     if (item >= a.num_items) return it;
-    const int b = (int)(item / a.items_per_tile);
-    const int r = (int)(item - (int64_t)b * a.items_per_tile);
+    const int b = (int)item / a.items_per_tile;  // (the launchers bound num_items to 31 bits: one 32-bit division)
+    const int r = (int)item - b * a.items_per_tile;
     it.b = b;
     int cx, cy;
     if (a.item_mode == kItemsCanvas) {
@@ -303,8 +303,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
     return ((uint64_t)hi << 32) | lo;
 }
 // cute::UMMA::InstrDescriptor: dense, fp32 accumulate, both operands K-major
-__device__ __forceinline__ uint32_t make_idesc(bool tf32, int m, int n) {
-    const uint32_t fmt = tf32 ? 2u : 1u;  // F16F32Format: TF32 = 2, BF16 = 1
+__device__ __forceinline__ uint32_t make_idesc(int fmt_code, int m, int n) {
+    const uint32_t fmt = (uint32_t)fmt_code;  // F16F32Format: F16 = 0, BF16 = 1, TF32 = 2
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // tcgen05.ld + tcgen05.wait::ld in ONE asm statement: the destination registers are only defined once the

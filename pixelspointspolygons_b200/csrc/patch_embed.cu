@@ -73,9 +73,15 @@ struct PeArgs {
 // with `nrows` rows starts at q * nrows * 128.  One 32-byte pixel run (c, py) of 8 fp32 values becomes
 //   tf32: 2 x 16-byte units  (chunk = k8 / 4, units (k8 % 4) * 2 + {0, 1}),   k8 = c * 8 + py
 //   bf16: 1 x 16-byte unit   (chunk = k8 / 8, unit k8 % 8)
-template <bool kTf32>
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+template <int kPrec>
 __device__ __forceinline__ void put_run(unsigned char* tile, int nrows, int row, int k8, const float4& lo, const float4& hi) {
-    if constexpr (kTf32) {
+    if constexpr (kPrec == P3P_PRECISION_TF32) {
         unsigned char* base = tile + (size_t)(k8 >> 2) * nrows * 128 + (size_t)row * 128;
         const int u = (k8 & 3) * 2;
         const uint4 a = make_uint4(to_tf32(lo.x), to_tf32(lo.y), to_tf32(lo.z), to_tf32(lo.w));
@@ -85,7 +91,9 @@ __device__ __forceinline__ void put_run(unsigned char* tile, int nrows, int row,
     } else {
         unsigned char* base = tile + (size_t)(k8 >> 3) * nrows * 128 + (size_t)row * 128;
         const int u = k8 & 7;
-        const uint4 a = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+        const uint4 a = (kPrec == P3P_PRECISION_BF16)
+                            ? make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w))
+                            : make_uint4(pack_f16(lo.x, lo.y), pack_f16(lo.z, lo.w), pack_f16(hi.x, hi.y), pack_f16(hi.z, hi.w));
         *reinterpret_cast<uint4*>(base + ((u ^ (row & 7)) * 16)) = a;
     }
 }
@@ -100,8 +108,9 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t taddr, float (&v)[16]) {
         : "memory");
 }
 
-template <bool kTf32>
+template <int kPrec>
 __global__ void __launch_bounds__(kPeThreads, 1) patch_embed_tc_kernel(PeArgs a) {
+    constexpr bool kTf32 = (kPrec == P3P_PRECISION_TF32);
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw = smem_u32(smem_dyn);
     unsigned char* base = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
@@ -163,9 +172,9 @@ __global__ void __launch_bounds__(kPeThreads, 1) patch_embed_tc_kernel(PeArgs a)
             for (int d = 0; d < kDepth; ++d) {
                 if (row[d] < 0) continue;
                 if (row[d] < 128)
-                    put_run<kTf32>(sA, 128, row[d], k8v[d], lo[d], hi[d]);
+                    put_run<kPrec>(sA, 128, row[d], k8v[d], lo[d], hi[d]);
                 else
-                    put_run<kTf32>(sB, Npad, row[d] - 128, k8v[d], lo[d], hi[d]);
+                    put_run<kPrec>(sB, Npad, row[d] - 128, k8v[d], lo[d], hi[d]);
             }
         }
     }
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(kPeThreads, 1) patch_embed_tc_kernel(PeArgs a)
 
     if (warp == 0) {
         if (elect_one()) {
-            const uint32_t idesc = make_idesc(kTf32, 128, a.N);
+            const uint32_t idesc = make_idesc(kTf32 ? 2 : (kPrec == P3P_PRECISION_BF16 ? 1 : 0), 128, a.N);
             const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, SWIZZLE_128B
             const uint32_t a_lo = (smem_u32(sA) >> 4) | (1u << 16), b_lo = (smem_u32(sB) >> 4) | (1u << 16);
             for (int q = 0; q < NQ; ++q) {
@@ -231,7 +240,7 @@ int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, i
                        int C, int precision, void* out, int out_dtype, int c_total, int c_offset, cudaStream_t st) {
     if (B <= 0) return P3P_OK;
     const int nx = W / P, ny = H / P;
-    const bool tf32 = (precision != P3P_PRECISION_BF16);
+    const bool tf32 = (precision != P3P_PRECISION_BF16 && precision != P3P_PRECISION_FP16);
     // tensor-core route: 8x8 patches; a row group of `rows` cell rows with rows * nx a multiple of 16 and <= 128 that
     // divides ny; operands (128 + N rows of K values) within the shared-memory budget; 16-byte aligned output rows
     int rows = 0;
@@ -248,8 +257,9 @@ int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, i
     if (rows > 0 && k_ok && smem <= 200 * 1024 && ((size_t)ny * nx * (out_dtype == P3P_DTYPE_F32 ? 4 : 2)) % 16 == 0) {
         static bool attr_done = false;
         if (!attr_done) {
-            P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<P3P_PRECISION_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<P3P_PRECISION_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<P3P_PRECISION_FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_done = true;
         }
         PeArgs a;
@@ -259,9 +269,11 @@ int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, i
         a.out_dtype = out_dtype; a.c_total = c_total; a.c_offset = c_offset;
         dim3 grid((unsigned)(ny / rows), (unsigned)((C + 127) / 128), (unsigned)B);
         if (tf32)
-            patch_embed_tc_kernel<true><<<grid, kPeThreads, smem, st>>>(a);
+            patch_embed_tc_kernel<P3P_PRECISION_TF32><<<grid, kPeThreads, smem, st>>>(a);
+        else if (precision == P3P_PRECISION_BF16)
+            patch_embed_tc_kernel<P3P_PRECISION_BF16><<<grid, kPeThreads, smem, st>>>(a);
         else
-            patch_embed_tc_kernel<false><<<grid, kPeThreads, smem, st>>>(a);
+            patch_embed_tc_kernel<P3P_PRECISION_FP16><<<grid, kPeThreads, smem, st>>>(a);
         P3P_CUDA_CHECK(cudaGetLastError());
         return P3P_OK;
     }

@@ -26,9 +26,27 @@
 //
 // pfn_simt_kernel: exact fp32 FMA, literal 8-channel formulation, any M and C -- the GPU-side cross-check of the
 // tensor-core path and the route for configurations the tensor-core kernel does not cover (density ablation).
+#include <cuda_fp16.h>
+
 #include "p3p_internal.cuh"
 
 namespace p3p {
+
+// Optional pipeline timeline (build with -DP3P_TIMELINE): lane 0 of the MMA warp, of every front-end warp and of the
+// first warp of every epilogue group stamps clock64 at its pipeline events; tools/pfn_timeline.py reads them back.
+#ifdef P3P_TIMELINE
+constexpr int kTlCtas = 4, kTlRoles = 12, kTlIters = 96, kTlStamps = 4;
+__device__ long long g_pfn_tl[kTlCtas][kTlRoles][kTlIters][kTlStamps];
+__device__ __forceinline__ void ptl(int role, long long it, int k) {
+    if ((threadIdx.x & 31) == 0 && blockIdx.x < kTlCtas && it < kTlIters) g_pfn_tl[blockIdx.x][role][it][k] = clock64();
+}
+#define PTL(role, it, k) ptl(role, it, k)
+extern "C" int p3p_debug_pfn_timeline(long long* host) {
+    return (int)cudaMemcpyFromSymbol(host, g_pfn_tl, sizeof(g_pfn_tl));
+}
+#else
+#define PTL(role, it, k)
+#endif
 
 void make_blob_layout(int C, BlobLayout* out) {
     BlobLayout l;
@@ -98,7 +116,7 @@ __global__ void pfn_prepare_kernel(p3p_pfn_params p, int precision, char* blob, 
             for (int r = 0; r < 10; ++r) front[r * 32 + k] *= up;
         }
     }
-    const bool tf32 = (precision != P3P_PRECISION_BF16);
+    const bool tf32 = (precision != P3P_PRECISION_BF16 && precision != P3P_PRECISION_FP16);
     for (int c = tid; c < bl.Cpad; c += nthreads) {
         float a = 0.f, sh = 0.f;
         if (c < bl.C) {
@@ -119,7 +137,9 @@ __global__ void pfn_prepare_kernel(p3p_pfn_params p, int precision, char* blob, 
             } else {
                 const size_t o = (size_t)t * 8192 + (size_t)(r >> 3) * 512 + (size_t)(r & 7) * 64 +
                                  (size_t)(((k >> 3) ^ ((r >> 1) & 3)) * 16) + (size_t)(k & 7) * 2;
-                *reinterpret_cast<unsigned short*>(tile + o) = (unsigned short)(pack_bf16(v, 0.f) & 0xFFFF);
+                *reinterpret_cast<unsigned short*>(tile + o) = (precision == P3P_PRECISION_FP16)
+                                                                   ? __half_as_ushort(__float2half_rn(v))
+                                                                   : (unsigned short)(pack_bf16(v, 0.f) & 0xFFFF);
             }
         }
     }
@@ -275,28 +295,30 @@ __global__ void zero_lidar_kernel(PfnArgs a) {
 // ------------------------------------------------------------------------------------------------
 // tensor-core kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kNF = 8;                         // front-end warps (one pillar each at a time)
-constexpr int kNS = kNF / 2;                   // B-operand stages: one pillar pair each
+constexpr int kNF = 8;                         // front-end warps: warp w takes item w of every unit
 constexpr int kEpiWarp0 = 1 + kNF;             // warp 0: TMEM alloc + MMA issue; 1..kNF: front end; then 12 epilogue warps
 constexpr int kTcThreads = 32 * (kEpiWarp0 + 12);
-constexpr int kUnit = 8;                       // items per epilogue flush (one 32-byte NCHW sector per channel)
+constexpr int kUnit = 8;                       // items per unit (one 32-byte NCHW sector per channel) = 4 pillar pairs
 constexpr int kPairsPerUnit = kUnit / 2;
-constexpr int kTmemStage = 160;  // TMEM columns per channel tile: 128 (pair) + 16 (G), padded
+constexpr int kBatchUnits = 2;                 // units per G batch: one N = 16 MMA gives W1b' hmax for 16 items
+constexpr int kBatchPairs = kBatchUnits * kPairsPerUnit;
+constexpr int kTmemStage = 144;                // TMEM columns per channel tile: 128 (pair) + 16 (G of a batch)
 
-template <bool kTf32>
+template <int kPrec>
 struct TcCfg {
+    static constexpr bool kTf32 = (kPrec == P3P_PRECISION_TF32);
+    static constexpr int kFmt = kTf32 ? 2 : (kPrec == P3P_PRECISION_BF16 ? 1 : 0);  // UMMA operand format code
     static constexpr int RB = kTf32 ? 128 : 64;           // bytes of one K = 32 operand row
     static constexpr int kATile = 128 * RB;               // 128 channels
     static constexpr int kHStage = 128 * RB;              // 2 pillars x 64 rows
-    static constexpr int kGStage = 16 * RB;               // N = 16 rows; rows 0,1 = hmax of the pair
+    static constexpr int kGStage = 16 * RB;               // hmax rows of the 16 items of a batch
     static constexpr uint32_t kLayout = kTf32 ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
     static constexpr uint32_t kSBO = 8 * RB;
-    static constexpr int kKSteps = kTf32 ? 4 : 2;         // UMMA_K = 8 (tf32) / 16 (bf16): 32 bytes per step
-    static constexpr int kGroup = kTf32 ? 4 : 8;          // channels per 16-byte operand chunk
-    static constexpr int kGroups = 32 / kGroup;
-    static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * (kHStage + kGStage);
-    static constexpr size_t kSmemFloats = 10 * 32 + 384 + kNF * 32;
-    static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + (2 * kNS + 8) * 8 + 16;
+    static constexpr int kKSteps = kTf32 ? 4 : 2;         // UMMA_K = 8 (tf32) / 16 (16-bit): 32 bytes per step
+    static constexpr int kNS = kTf32 ? 4 : 8;             // B-operand stages: pillar pairs in flight
+    static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * kHStage + 2 * (size_t)kGStage;
+    static constexpr size_t kSmemFloats = 10 * 32 + 384 + kNF * 64 * 4;
+    static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + (2 * kNS + 16) * 8 + 16;
 };
 
 __device__ __forceinline__ float max32(const float (&v)[32]) {
@@ -307,49 +329,126 @@ __device__ __forceinline__ float max32(const float (&v)[32]) {
     return fmaxf(fmax3(fmax3(r[0], r[1], r[2]), fmax3(r[3], r[4], r[5]), fmax3(r[6], r[7], r[8])), fmaxf(r[9], r[10]));
 }
 
-__device__ __forceinline__ float max64(const float (&v)[64]) {
-    float r[22];
-#pragma unroll
-    for (int i = 0; i < 21; ++i) r[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-    r[21] = v[63];
-    float s[8];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) s[i] = fmax3(r[3 * i], r[3 * i + 1], r[3 * i + 2]);
-    s[7] = r[21];
-    return fmaxf(fmax3(s[0], s[1], s[2]), fmax3(fmax3(s[3], s[4], s[5]), s[6], s[7]));
+// two fp32 -> packed 16-bit pair with relu fused into the conversion (lo = first channel)
+template <int kPrec>
+__device__ __forceinline__ uint32_t pack_relu16(float lo, float hi) {
+    uint32_t r;
+    if constexpr (kPrec == P3P_PRECISION_BF16)
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <int kPrec>
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    if constexpr (kPrec == P3P_PRECISION_BF16)
+        asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    else
+        asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
 }
 
-template <bool kTf32>
+// item -> (tile, position inside the tile) for the 8 items of a unit with ONE 32-bit division
+struct UnitLoc {
+    int b0, r0;  // of the unit's first item
+};
+__device__ __forceinline__ UnitLoc locate_unit(const PfnArgs& a, int item0) {
+    UnitLoc u;
+    u.b0 = item0 / a.items_per_tile;
+    u.r0 = item0 - u.b0 * a.items_per_tile;
+    return u;
+}
+// validity bits of the 8 items of a unit (bit i: item0 + i holds a pillar)
+__device__ __forceinline__ unsigned unit_valid_mask(const PfnArgs& a, int item0, const UnitLoc& u) {
+    unsigned vmask = 0;
+    const int total = (int)a.num_items;
+    if (a.item_mode == kItemsCanvas) {
+        if (item0 + kUnit <= total) {  // item0 is a multiple of 8: two aligned 16-byte loads
+            const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.ws.cell_desc + item0));
+            const int4 d1 = __ldg(reinterpret_cast<const int4*>(a.ws.cell_desc + item0) + 1);
+            vmask = (d0.x >= 0 ? 1u : 0u) | (d0.y >= 0 ? 2u : 0u) | (d0.z >= 0 ? 4u : 0u) | (d0.w >= 0 ? 8u : 0u) |
+                    (d1.x >= 0 ? 16u : 0u) | (d1.y >= 0 ? 32u : 0u) | (d1.z >= 0 ? 64u : 0u) | (d1.w >= 0 ? 128u : 0u);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kUnit; ++i)
+                if (item0 + i < total && __ldg(a.ws.cell_desc + item0 + i) >= 0) vmask |= 1u << i;
+        }
+    } else {
+        int b = u.b0, r = u.r0;
+        int np = (item0 < total) ? a.ws.num_pil[b] : 0;
+#pragma unroll
+        for (int i = 0; i < kUnit; ++i) {
+            if (item0 + i < total && r < np) vmask |= 1u << i;
+            if (++r == a.items_per_tile) {
+                r = 0;
+                ++b;
+                np = (item0 + i + 1 < total) ? a.ws.num_pil[b] : 0;
+            }
+        }
+    }
+    return vmask;
+}
+
+template <int kPrec>
 __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
-    using Cfg = TcCfg<kTf32>;
+    using Cfg = TcCfg<kPrec>;
+    constexpr bool kTf32 = Cfg::kTf32;
+    constexpr int kNS = Cfg::kNS;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw = smem_u32(smem_dyn);
     unsigned char* base = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
     unsigned char* sA1 = base;
     unsigned char* sA2 = sA1 + 3 * Cfg::kATile;
     unsigned char* sH = sA2 + 3 * Cfg::kATile;
-    unsigned char* sG = sH + kNS * Cfg::kHStage;
-    float* sFront = reinterpret_cast<float*>(sG + kNS * Cfg::kGStage);  // [10][32]
+    unsigned char* sG = sH + kNS * Cfg::kHStage;                        // [2 batch slots][16 rows]
+    float* sFront = reinterpret_cast<float*>(sG + 2 * Cfg::kGStage);    // [10][32]
     float* sB1 = sFront + 10 * 32;                                      // [384]
-    float* sKap = sB1 + 384;                                            // [kNF][32]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sKap + kNF * 32);
-    uint64_t* h_full = bars;                 // [kNS] front end -> MMA (2 arrivals: the two warps of a pair)
-    uint64_t* h_empty = bars + kNS;          // [kNS] MMA -> front end (tcgen05.commit)
-    uint64_t* t_full = bars + 2 * kNS;       // [3]   MMA -> epilogue group m (tcgen05.commit)
-    uint64_t* t_empty = bars + 2 * kNS + 3;  // [3]   epilogue group m -> MMA (128 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 6);
+    float4* sPts = reinterpret_cast<float4*>(sB1 + 384);                // [kNF][64] centred points of the pillar in work
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPts + kNF * 64);
+    uint64_t* h_full = bars;                  // [kNS] front end -> MMA (2 arrivals: the two warps of a pair)
+    uint64_t* h_empty = bars + kNS;           // [kNS] MMA -> front end (tcgen05.commit)
+    uint64_t* t_full = bars + 2 * kNS;        // [3]   MMA -> epilogue group m (tcgen05.commit), per pair
+    uint64_t* t_empty = t_full + 3;           // [3]   epilogue group m -> MMA (128 arrivals)
+    uint64_t* gt_full = t_empty + 3;          // [3]   MMA -> epilogue group m, per batch (G accumulator)
+    uint64_t* gt_empty = gt_full + 3;         // [3]   epilogue group m -> MMA (128 arrivals)
+    uint64_t* g_empty = gt_empty + 3;         // [2]   MMA -> front end: hmax rows of the batch slot consumed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int MT = a.bl.MT;
-    const int64_t num_units = (a.num_items + kUnit - 1) / kUnit;
-    const int64_t my_units = (num_units > blockIdx.x) ? (num_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t my_pairs = my_units * kPairsPerUnit;  // pairs this CTA processes, in order p = 0, 1, ...
+    const int total_items = (int)a.num_items;
+    const int num_units = (total_items + kUnit - 1) / kUnit;
+    const int my_units = (num_units > (int)blockIdx.x) ? (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int my_pairs = my_units * kPairsPerUnit;  // pairs this CTA processes, in order p = 0, 1, ...
 
     // ---- one-time setup --------------------------------------------------------------------------
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
         for (int i = 0; i < kNS; ++i) { mbar_init(&h_full[i], 2); mbar_init(&h_empty[i], 1); }
-        for (int i = 0; i < 3; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128);
+            mbar_init(&gt_full[i], 1); mbar_init(&gt_empty[i], 128);
+        }
+        mbar_init(&g_empty[0], 1); mbar_init(&g_empty[1], 1);
         fence_mbar_init();
     }
     {
@@ -360,7 +459,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             reinterpret_cast<uint4*>(sA1)[i] = g1[i];
             reinterpret_cast<uint4*>(sA2)[i] = g2[i];
         }
-        for (int i = tid; i < kNS * Cfg::kGStage / 16; i += kTcThreads) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < 2 * Cfg::kGStage / 16; i += kTcThreads) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0, 0, 0, 0);
         const float* fg = reinterpret_cast<const float*>(a.blob + a.bl.off_front);
         const float* b1g = reinterpret_cast<const float*>(a.blob + a.bl.off_b1);
         for (int i = tid; i < 10 * 32; i += kTcThreads) sFront[i] = fg[i];
@@ -377,28 +476,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers);
         // one elected lane issues the tcgen05 instructions and their commits.
         const bool leader = elect_one();
-        const uint32_t idesc_main = make_idesc(kTf32, 128, 128);
-        const uint32_t idesc_g = make_idesc(kTf32, 128, 16);
+        const uint32_t idesc_main = make_idesc(Cfg::kFmt, 128, 128);
+        const uint32_t idesc_g = make_idesc(Cfg::kFmt, 128, 16);
         const uint32_t desc_hi = (Cfg::kSBO >> 4) | (1u << 14) | (Cfg::kLayout << 29);
         const uint32_t a1_lo = (smem_u32(sA1) >> 4) | (1u << 16), a2_lo = (smem_u32(sA2) >> 4) | (1u << 16);
         const uint32_t h_lo = (smem_u32(sH) >> 4) | (1u << 16), g_lo = (smem_u32(sG) >> 4) | (1u << 16);
         int st = 0;
         uint32_t use = 0;
-        for (int64_t p = 0; p < my_pairs; ++p) {
+        for (int p = 0; p < my_pairs; ++p) {
             mbar_wait(&h_full[st], use & 1);
+            PTL(0, p, 0);
             tc_fence_after();
-            const uint32_t hs_lo = h_lo + (uint32_t)st * (Cfg::kHStage >> 4), gs_lo = g_lo + (uint32_t)st * (Cfg::kGStage >> 4);
+            const uint32_t hs_lo = h_lo + (uint32_t)st * (Cfg::kHStage >> 4);
 #pragma unroll
             for (int m = 0; m < 3; ++m) {
                 if (m < MT) {
                     mbar_wait(&t_empty[m], ((uint32_t)p & 1) ^ 1);
+                    PTL(0, p, 1 + m);
                     tc_fence_after();
                     if (leader) {
-                        const uint32_t d_main = tmem_base + m * kTmemStage, d_g = d_main + 128;
-#pragma unroll
-                        for (int k = 0; k < Cfg::kKSteps; ++k)
-                            tc_mma<kTf32>(d_g, ((uint64_t)desc_hi << 32) | (a2_lo + (uint32_t)((m * Cfg::kATile + k * 32) >> 4)),
-                                          ((uint64_t)desc_hi << 32) | (gs_lo + (uint32_t)(k * 2)), idesc_g, k > 0);
+                        const uint32_t d_main = tmem_base + m * kTmemStage;
 #pragma unroll
                         for (int k = 0; k < Cfg::kKSteps; ++k)
                             tc_mma<kTf32>(d_main, ((uint64_t)desc_hi << 32) | (a1_lo + (uint32_t)((m * Cfg::kATile + k * 32) >> 4)),
@@ -411,28 +508,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             if (leader) tc_commit(&h_empty[st]);
             __syncwarp();
             if (++st == kNS) { st = 0; ++use; }
+            // ---- end of a batch (16 items): G = W1b' hmax for all of them with one N = 16 MMA chain per channel tile ----
+            if ((p & (kBatchPairs - 1)) == kBatchPairs - 1 || p == my_pairs - 1) {
+                const uint32_t bt = (uint32_t)p / kBatchPairs, slot = bt & 1u;
+                const uint32_t gs_lo = g_lo + slot * (Cfg::kGStage >> 4);
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    if (m < MT) {
+                        mbar_wait(&gt_empty[m], (bt & 1u) ^ 1u);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t d_g = tmem_base + m * kTmemStage + 128;
+#pragma unroll
+                            for (int k = 0; k < Cfg::kKSteps; ++k)
+                                tc_mma<kTf32>(d_g, ((uint64_t)desc_hi << 32) | (a2_lo + (uint32_t)((m * Cfg::kATile + k * 32) >> 4)),
+                                              ((uint64_t)desc_hi << 32) | (gs_lo + (uint32_t)(k * 2)), idesc_g, k > 0);
+                            tc_commit(&gt_full[m]);
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (leader) tc_commit(&g_empty[slot]);
+                __syncwarp();
+            }
         }
     } else if (warp < kEpiWarp0) {
-        // =========================== front end: one pillar per warp ===========================
-        const int fw = warp - 1, half = fw & 1, st = fw >> 1;  // this warp fills half `half` of stage `st`
-        const float2* Ux2 = reinterpret_cast<const float2*>(sFront + 0 * 32);
-        const float2* Uy2 = reinterpret_cast<const float2*>(sFront + 1 * 32);
-        const float2* Uz2 = reinterpret_cast<const float2*>(sFront + 2 * 32);
-        const float4* Hp4 = reinterpret_cast<const float4*>(sFront + 9 * 32);
-        float* kap = sKap + fw * 32;
-        const float2* Kp2 = reinterpret_cast<const float2*>(kap);
-        const float kcx = sFront[3 * 32 + lane], kcy = sFront[4 * 32 + lane];
-        const float wmx = sFront[5 * 32 + lane], wmy = sFront[6 * 32 + lane], wmz = sFront[7 * 32 + lane];
-        const float b0l = sFront[8 * 32 + lane];
+        // =========================== front end: warp fw takes item fw of every unit ===========================
+        // lane = (channel pair cp, point parity par): 32 steps over the pillar's 64 slots, 2 channels x 1 point per lane
+        // and step; the point comes from shared memory (broadcast), the channel constants sit in registers.
+        const int fw = warp - 1, half = fw & 1, pr = fw >> 1;
+        const int cp = lane & 15, par = lane >> 4;
+        auto cst = [&](int row) { return *reinterpret_cast<const float2*>(sFront + row * 32 + 2 * cp); };
+        const float2 ux = cst(0), uy = cst(1), uz = cst(2), kcx = cst(3), kcy = cst(4), wmx = cst(5), wmy = cst(6), wmz = cst(7),
+                     b0v = cst(8), hpv = cst(9);
+        float4* pts = sPts + fw * 64;
+        const uint32_t pts_sa = smem_u32(pts) + (uint32_t)par * 16u;
+        // byte offset of this lane's channel pair inside an operand row, per swizzle phase of the row
+        uint32_t uoff[4];
+        uint32_t hpad16 = 0;
+        if constexpr (kTf32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) uoff[j] = (uint32_t)((((cp >> 1) ^ ((j << 1) | par)) * 16) + (cp & 1) * 8);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) uoff[j] = (uint32_t)((((cp >> 2) ^ j) * 16) + (cp & 3) * 4);
+            hpad16 = pack_relu16<kPrec>(hpv.x, hpv.y);
+        }
+        const uint32_t hrow0 = (uint32_t)(half * 64 + par) * Cfg::RB;  // row of step 0 inside a stage
 
-        // this warp's pairs: p = st, st + kNS, ...; pair p covers items 2p, 2p+1 of the CTA's unit sequence
-        auto item_of = [&](int64_t j) -> int64_t {
-            const int64_t p = st + j * kNS;
-            if (p >= my_pairs) return a.num_items;  // fetch_item -> invalid
-            const int64_t u = blockIdx.x + (p / kPairsPerUnit) * (int64_t)gridDim.x;
-            return u * kUnit + (p % kPairsPerUnit) * 2 + half;
-        };
-        const int64_t nseq = (my_pairs > st) ? (my_pairs - st + kNS - 1) / kNS : 0;
+        auto item_of = [&](int j) -> int { return (j < my_units) ? ((int)blockIdx.x + j * (int)gridDim.x) * kUnit + fw : total_items; };
         // software pipeline: descriptor two ahead, points one ahead
         Item it_cur = fetch_item(a, item_of(0));
         Item it_nxt = fetch_item(a, item_of(1));
@@ -442,10 +566,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             if (lane < it_cur.n) c0 = sl[lane];
             if (lane + 32 < it_cur.n) c1 = sl[lane + 32];
         }
-        unsigned char* hst = sH + st * Cfg::kHStage;
-        unsigned char* gst = sG + st * Cfg::kGStage;
-        const int R0 = half * 64 + lane, R1 = R0 + 32;
-        for (int64_t j = 0; j < nseq; ++j) {
+        for (int j = 0; j < my_units; ++j) {
             const Item it = it_cur;
             const float4 p0 = c0, p1 = c1;
             it_cur = it_nxt;
@@ -457,7 +578,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             }
             it_nxt = fetch_item(a, item_of(j + 2));
 
-            mbar_wait(&h_empty[st], ((uint32_t)j & 1) ^ 1);
+            const int p = j * kPairsPerUnit + pr, st = p % kNS;
+            const uint32_t use = (uint32_t)(p / kNS), bt = (uint32_t)j / kBatchUnits, slot = bt & 1u;
+            const int grow = ((j & (kBatchUnits - 1)) * kPairsPerUnit + pr) * 2 + half;  // row of this item in the batch's G operand
+            PTL(1 + fw, j, 0);
+            mbar_wait(&h_empty[st], (use & 1u) ^ 1u);
+            mbar_wait(&g_empty[slot], ((bt >> 1) & 1u) ^ 1u);
+            PTL(1 + fw, j, 1);
             if (it.valid) {
                 const int n = it.n;
                 float mean3[3];
@@ -473,58 +600,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                     }
                 }
                 const float mpx = mean3[0] - it.ctr_x, mpy = mean3[1] - it.ctr_y, mz = mean3[2];
-                float kv = b0l;
-                kv = __fmaf_rn(kcx, it.ctr_x, kv);
-                kv = __fmaf_rn(kcy, it.ctr_y, kv);
-                kv = __fmaf_rn(-wmx, mpx, kv);
-                kv = __fmaf_rn(-wmy, mpy, kv);
-                kv = __fmaf_rn(-wmz, mz, kv);
-                kap[lane] = kv;
+                float2 kap;
+                kap.x = __fmaf_rn(-wmz.x, mz, __fmaf_rn(-wmy.x, mpy, __fmaf_rn(-wmx.x, mpx, __fmaf_rn(kcy.x, it.ctr_y, __fmaf_rn(kcx.x, it.ctr_x, b0v.x)))));
+                kap.y = __fmaf_rn(-wmz.y, mz, __fmaf_rn(-wmy.y, mpy, __fmaf_rn(-wmx.y, mpx, __fmaf_rn(kcy.y, it.ctr_y, __fmaf_rn(kcx.y, it.ctr_x, b0v.y)))));
+                pts[lane] = make_float4(p0.x - it.ctr_x, p0.y - it.ctr_y, p0.z, 0.f);
+                pts[lane + 32] = make_float4(p1.x - it.ctr_x, p1.y - it.ctr_y, p1.z, 0.f);
                 __syncwarp();
-                const float2 x0 = make_float2(p0.x - it.ctr_x, p0.x - it.ctr_x), y0 = make_float2(p0.y - it.ctr_y, p0.y - it.ctr_y);
-                const float2 z0 = make_float2(p0.z, p0.z);
-                const float2 x1 = make_float2(p1.x - it.ctr_x, p1.x - it.ctr_x), y1 = make_float2(p1.y - it.ctr_y, p1.y - it.ctr_y);
-                const float2 z1 = make_float2(p1.z, p1.z);
-                const bool ok0 = lane < n, ok1 = lane + 32 < n;
+                const uint32_t hst_sa = smem_u32(sH) + (uint32_t)st * Cfg::kHStage + hrow0;
+                const uint32_t g_sa = smem_u32(sG) + slot * Cfg::kGStage + (uint32_t)grow * Cfg::RB;
+                if constexpr (kTf32) {
+                    float m0 = 0.f, m1 = 0.f;
 #pragma unroll
-                for (int g = 0; g < Cfg::kGroups; ++g) {
-                    float h0[Cfg::kGroup], h1[Cfg::kGroup], hm[Cfg::kGroup];
-#pragma unroll
-                    for (int v2 = 0; v2 < Cfg::kGroup / 2; ++v2) {
-                        const int i2 = g * (Cfg::kGroup / 2) + v2;
-                        const float2 ux = Ux2[i2], uy = Uy2[i2], uz = Uz2[i2], kp = Kp2[i2];
-                        const float2 a0 = ffma2(ux, x0, ffma2(uy, y0, ffma2(uz, z0, kp)));
-                        const float2 a1 = ffma2(ux, x1, ffma2(uy, y1, ffma2(uz, z1, kp)));
-                        h0[v2 * 2 + 0] = fmaxf(a0.x, 0.f); h0[v2 * 2 + 1] = fmaxf(a0.y, 0.f);
-                        h1[v2 * 2 + 0] = fmaxf(a1.x, 0.f); h1[v2 * 2 + 1] = fmaxf(a1.y, 0.f);
-                    }
-                    if (n < 64) {  // padded slots carry relu(BN(0)) (warp-uniform branch)
-#pragma unroll
-                        for (int v4 = 0; v4 < Cfg::kGroup / 4; ++v4) {
-                            const float4 hp = Hp4[g * (Cfg::kGroup / 4) + v4];
-                            if (!ok0) { h0[v4 * 4 + 0] = hp.x; h0[v4 * 4 + 1] = hp.y; h0[v4 * 4 + 2] = hp.z; h0[v4 * 4 + 3] = hp.w; }
-                            if (!ok1) { h1[v4 * 4 + 0] = hp.x; h1[v4 * 4 + 1] = hp.y; h1[v4 * 4 + 2] = hp.z; h1[v4 * 4 + 3] = hp.w; }
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < Cfg::kGroup; ++i) hm[i] = warp_max_f32(fmaxf(h0[i], h1[i]));
-                    if constexpr (kTf32) {
+                    for (int s = 0; s < 32; ++s) {
+                        const float4 q = lds128(pts_sa + (uint32_t)s * 32u);
+                        const float2 v = ffma2(ux, make_float2(q.x, q.x), ffma2(uy, make_float2(q.y, q.y), ffma2(uz, make_float2(q.z, q.z), kap)));
+                        float h0 = fmaxf(v.x, 0.f), h1 = fmaxf(v.y, 0.f);
+                        if (n < 64 && 2 * s + par >= n) { h0 = hpv.x; h1 = hpv.y; }  // padded slots carry relu(BN(0))
+                        m0 = fmaxf(m0, h0); m1 = fmaxf(m1, h1);
                         // operands are already scaled by (1 + 2^-12): the MMA's truncation rounds them to nearest tf32
-                        *reinterpret_cast<float4*>(hst + R0 * 128 + ((g ^ (R0 & 7)) * 16)) = make_float4(h0[0], h0[1], h0[2], h0[3]);
-                        *reinterpret_cast<float4*>(hst + R1 * 128 + ((g ^ (R1 & 7)) * 16)) = make_float4(h1[0], h1[1], h1[2], h1[3]);
-                        if (lane == 0) *reinterpret_cast<float4*>(gst + half * 128 + ((g ^ half) * 16)) = make_float4(hm[0], hm[1], hm[2], hm[3]);
-                    } else {
-                        const uint4 w0v = make_uint4(pack_bf16(h0[0], h0[1]), pack_bf16(h0[2], h0[3]), pack_bf16(h0[4], h0[5]), pack_bf16(h0[6], h0[7]));
-                        const uint4 w1v = make_uint4(pack_bf16(h1[0], h1[1]), pack_bf16(h1[2], h1[3]), pack_bf16(h1[4], h1[5]), pack_bf16(h1[6], h1[7]));
-                        const uint4 wmv = make_uint4(pack_bf16(hm[0], hm[1]), pack_bf16(hm[2], hm[3]), pack_bf16(hm[4], hm[5]), pack_bf16(hm[6], hm[7]));
-                        *reinterpret_cast<uint4*>(hst + R0 * 64 + ((g ^ ((R0 >> 1) & 3)) * 16)) = w0v;
-                        *reinterpret_cast<uint4*>(hst + R1 * 64 + ((g ^ ((R1 >> 1) & 3)) * 16)) = w1v;
-                        if (lane == 0) *reinterpret_cast<uint4*>(gst + half * 64 + (g * 16)) = wmv;
+                        sts64(hst_sa + (uint32_t)s * (2u * Cfg::RB) + uoff[s & 3], h0, h1);
                     }
+                    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 16));
+                    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 16));
+                    if (par == 0) sts64(g_sa + (uint32_t)((((cp >> 1) ^ (grow & 7)) * 16) + (cp & 1) * 8), m0, m1);
+                } else {
+                    uint32_t mm = 0;
+#pragma unroll
+                    for (int s = 0; s < 32; ++s) {
+                        const float4 q = lds128(pts_sa + (uint32_t)s * 32u);
+                        const float2 v = ffma2(ux, make_float2(q.x, q.x), ffma2(uy, make_float2(q.y, q.y), ffma2(uz, make_float2(q.z, q.z), kap)));
+                        uint32_t h = pack_relu16<kPrec>(v.x, v.y);
+                        if (n < 64 && 2 * s + par >= n) h = hpad16;
+                        mm = max16x2<kPrec>(mm, h);
+                        sts32(hst_sa + (uint32_t)s * (2u * Cfg::RB) + uoff[s & 3], h);
+                    }
+                    mm = max16x2<kPrec>(mm, __shfl_xor_sync(0xffffffffu, mm, 16));
+                    if (par == 0) sts32(g_sa + (uint32_t)((((cp >> 2) ^ ((grow >> 1) & 3)) * 16) + (cp & 3) * 4), mm);
                 }
             }
             fence_async_smem();
             __syncwarp();
+            PTL(1 + fw, j, 2);
             if (lane == 0) mbar_arrive(&h_full[st]);
         }
     } else {
@@ -538,68 +654,87 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(m * kTmemStage);
             const bool nchw = (a.item_mode == kItemsCanvas) && (a.out_layout == P3P_LAYOUT_NCHW);
             const bool nchw_vec = nchw && (a.items_per_tile % kUnit == 0);
-            uint32_t gp = 0;
-            for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
-                float ob[kUnit];
-                const int64_t item0 = u * kUnit;
-                unsigned vmask = 0;
+            uint32_t gp = 0, bt = 0;
+            for (int j0 = 0; j0 < my_units; j0 += kBatchUnits, ++bt) {
+                const int nun = (my_units - j0 < kBatchUnits) ? my_units - j0 : kBatchUnits;
+                // where the batch's units go and which of their items exist (loads in flight during the pair loop)
+                int item0[kBatchUnits];
+                UnitLoc loc[kBatchUnits];
+                unsigned vmask[kBatchUnits];
 #pragma unroll
-                for (int i = 0; i < kUnit; ++i) {
-                    const int64_t item = item0 + i;
-                    bool v = false;
-                    if (item < a.num_items) {
-                        if (a.item_mode == kItemsCanvas) {
-                            v = __ldg(a.ws.cell_desc + item) >= 0;
-                        } else {
-                            const int b = (int)(item / a.items_per_tile);
-                            v = (int)(item - (int64_t)b * a.items_per_tile) < a.ws.num_pil[b];
-                        }
+                for (int uu = 0; uu < kBatchUnits; ++uu) {
+                    item0[uu] = ((int)blockIdx.x + (j0 + uu) * (int)gridDim.x) * kUnit;
+                    loc[uu].b0 = 0; loc[uu].r0 = 0;
+                    vmask[uu] = 0;
+                    if (uu < nun) {
+                        loc[uu] = locate_unit(a, item0[uu]);
+                        vmask[uu] = unit_valid_mask(a, item0[uu], loc[uu]);
                     }
-                    vmask |= (v ? 1u : 0u) << i;
                 }
+                float rmax[kBatchUnits * kUnit];
 #pragma unroll
-                for (int q = 0; q < kPairsPerUnit; ++q, ++gp) {
-                    mbar_wait(&t_full[m], gp & 1);
-                    tc_fence_after();
-                    float v[32];
-                    tmem_ld32_wait(taddr + 0, v);
-                    float mA = max32(v);
-                    tmem_ld32_wait(taddr + 32, v);
-                    mA = fmaxf(mA, max32(v));
-                    tmem_ld32_wait(taddr + 64, v);
-                    float mB = max32(v);
-                    tmem_ld32_wait(taddr + 96, v);
-                    mB = fmaxf(mB, max32(v));
-                    float gA, gB;
-                    tmem_ld2_wait(taddr + 128, gA, gB);
-                    tc_fence_before();
-                    mbar_arrive(&t_empty[m]);
-                    ob[2 * q + 0] = ((vmask >> (2 * q)) & 1u) ? fmaxf(mA + gA + b1c, 0.f) : 0.f;
-                    ob[2 * q + 1] = ((vmask >> (2 * q + 1)) & 1u) ? fmaxf(mB + gB + b1c, 0.f) : 0.f;
+                for (int q = 0; q < kBatchPairs; ++q) {
+                    rmax[2 * q] = 0.f; rmax[2 * q + 1] = 0.f;
+                    if (q < nun * kPairsPerUnit) {  // warp-uniform
+                        if (quad == 0) PTL(9 + m, gp, 0);
+                        mbar_wait(&t_full[m], gp & 1);
+                        if (quad == 0) PTL(9 + m, gp, 1);
+                        tc_fence_after();
+                        float v[32];
+                        tmem_ld32_wait(taddr + 0, v);
+                        float mA = max32(v);
+                        tmem_ld32_wait(taddr + 32, v);
+                        mA = fmaxf(mA, max32(v));
+                        tmem_ld32_wait(taddr + 64, v);
+                        float mB = max32(v);
+                        tmem_ld32_wait(taddr + 96, v);
+                        mB = fmaxf(mB, max32(v));
+                        tc_fence_before();
+                        mbar_arrive(&t_empty[m]);
+                        if (quad == 0) PTL(9 + m, gp, 2);
+                        rmax[2 * q] = mA; rmax[2 * q + 1] = mB;
+                        ++gp;
+                    }
                 }
+                float g[16];
+                mbar_wait(&gt_full[m], bt & 1);
+                tc_fence_after();
+                tmem_ld16_wait(taddr + 128, g);
+                tc_fence_before();
+                mbar_arrive(&gt_empty[m]);
+                if (quad == 0) PTL(9 + m, gp - 1, 3);
                 if (!c_ok) continue;
-                if (nchw_vec) {
-                    const int b = (int)(item0 / a.items_per_tile);
-                    const int cell0 = (int)(item0 - (int64_t)b * a.items_per_tile);
-                    const int64_t idx = ((int64_t)b * a.c_total + a.c_offset + c) * a.items_per_tile + cell0;
-                    if (a.out_dtype == P3P_DTYPE_F32) {
-                        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(a.out) + idx);
-                        dst[0] = make_float4(ob[0], ob[1], ob[2], ob[3]);
-                        dst[1] = make_float4(ob[4], ob[5], ob[6], ob[7]);
-                    } else {
-                        uint4* dst = reinterpret_cast<uint4*>(static_cast<unsigned short*>(a.out) + idx);
-                        dst[0] = make_uint4(pack_bf16(ob[0], ob[1]), pack_bf16(ob[2], ob[3]), pack_bf16(ob[4], ob[5]), pack_bf16(ob[6], ob[7]));
-                    }
-                } else {
 #pragma unroll
-                    for (int i = 0; i < kUnit; ++i) {
-                        const int64_t item = item0 + i;
-                        if (item >= a.num_items) break;
-                        const bool v = (vmask >> i) & 1u;
-                        if (!v && a.item_mode != kItemsCanvas) continue;  // list rows past num_pillars stay untouched
-                        const int b = (int)(item / a.items_per_tile);
-                        const int cell = (int)(item - (int64_t)b * a.items_per_tile);
-                        store_scalar(a, out_index(a, item, b, cell, c), ob[i]);
+                for (int uu = 0; uu < kBatchUnits; ++uu) {
+                    if (uu >= nun) break;
+                    float ob[kUnit];
+#pragma unroll
+                    for (int i = 0; i < kUnit; ++i)
+                        ob[i] = ((vmask[uu] >> i) & 1u) ? fmaxf(rmax[uu * kUnit + i] + g[uu * kUnit + i] + b1c, 0.f) : 0.f;
+                    if (nchw_vec) {
+                        const int64_t idx = ((int64_t)loc[uu].b0 * a.c_total + a.c_offset + c) * a.items_per_tile + loc[uu].r0;
+                        if (a.out_dtype == P3P_DTYPE_F32) {
+                            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(a.out) + idx);
+                            dst[0] = make_float4(ob[0], ob[1], ob[2], ob[3]);
+                            dst[1] = make_float4(ob[4], ob[5], ob[6], ob[7]);
+                        } else {
+                            uint4* dst = reinterpret_cast<uint4*>(static_cast<unsigned short*>(a.out) + idx);
+                            dst[0] = make_uint4(pack_bf16(ob[0], ob[1]), pack_bf16(ob[2], ob[3]), pack_bf16(ob[4], ob[5]), pack_bf16(ob[6], ob[7]));
+                        }
+                    } else {
+                        int b = loc[uu].b0, r = loc[uu].r0;
+#pragma unroll
+                        for (int i = 0; i < kUnit; ++i) {
+                            const int item = item0[uu] + i;
+                            const bool v = (vmask[uu] >> i) & 1u;
+                            // list rows past num_pillars stay untouched; canvas cells are always written
+                            if (item < total_items && (v || a.item_mode == kItemsCanvas)) {
+                                const int64_t idx = nchw ? ((int64_t)b * a.c_total + a.c_offset + c) * a.items_per_tile + r
+                                                         : (int64_t)item * a.bl.C + c;
+                                store_scalar(a, idx, ob[i]);
+                            }
+                            if (++r == a.items_per_tile) { r = 0; ++b; }
+                        }
                     }
                 }
             }
@@ -620,6 +755,7 @@ int launch_pfn_prepare(const p3p_pfn_params* p, int precision, char* blob, const
 
 int launch_pfn_simt(const PfnArgs& a, cudaStream_t st) {
     if (a.num_items <= 0) return P3P_OK;
+    if (a.num_items > 0x7fffffff - 64) return fail(P3P_ERR_UNSUPPORTED, "%lld work items exceed the 32-bit item index", (long long)a.num_items);
     const size_t smem = ((size_t)(a.g.M + 1) * kHStride + 256 + 32 + 24 + 32) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
@@ -643,21 +779,26 @@ int launch_zero_lidar(const PfnArgs& a, cudaStream_t st) {
 
 int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st) {
     if (a.num_items <= 0) return P3P_OK;
+    if (a.num_items > 0x7fffffff - 64) return fail(P3P_ERR_UNSUPPORTED, "%lld work items exceed the 32-bit item index", (long long)a.num_items);
     static bool attr_done = false;
     if (!attr_done) {
-        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)TcCfg<true>::kSmemBytes));
-        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)TcCfg<false>::kSmemBytes));
+        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<P3P_PRECISION_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)TcCfg<P3P_PRECISION_TF32>::kSmemBytes));
+        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<P3P_PRECISION_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)TcCfg<P3P_PRECISION_BF16>::kSmemBytes));
+        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<P3P_PRECISION_FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)TcCfg<P3P_PRECISION_FP16>::kSmemBytes));
         attr_done = true;
     }
     const int64_t units = (a.num_items + kUnit - 1) / kUnit;
     int64_t grid = device_sm_count();
     if (grid > units) grid = units;
     if (precision == P3P_PRECISION_TF32)
-        pfn_tc_kernel<true><<<(unsigned)grid, kTcThreads, TcCfg<true>::kSmemBytes, st>>>(a);
+        pfn_tc_kernel<P3P_PRECISION_TF32><<<(unsigned)grid, kTcThreads, TcCfg<P3P_PRECISION_TF32>::kSmemBytes, st>>>(a);
+    else if (precision == P3P_PRECISION_BF16)
+        pfn_tc_kernel<P3P_PRECISION_BF16><<<(unsigned)grid, kTcThreads, TcCfg<P3P_PRECISION_BF16>::kSmemBytes, st>>>(a);
     else
-        pfn_tc_kernel<false><<<(unsigned)grid, kTcThreads, TcCfg<false>::kSmemBytes, st>>>(a);
+        pfn_tc_kernel<P3P_PRECISION_FP16><<<(unsigned)grid, kTcThreads, TcCfg<P3P_PRECISION_FP16>::kSmemBytes, st>>>(a);
     P3P_CUDA_CHECK(cudaGetLastError());
     return P3P_OK;
 }

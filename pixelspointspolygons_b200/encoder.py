@@ -110,12 +110,13 @@ class PointPillarsEncoder(nn.Module):
         self.voxel_encoder = PillarFeatureNet(3, feat_channels, voxel_size, self.point_cloud_range)
         self.center_alias = bool(_get(enc, "p3p_center_alias", True))          # DESIGN.md ledger U2
         self.drop_overflow = bool(_get(enc, "p3p_drop_overflow", False))       # DESIGN.md ledger U1
-        self.precision = str(_get(enc, "p3p_precision", None) or os.environ.get("P3P_PRECISION", "tf32")).lower()
+        self.precision = str(_get(enc, "p3p_precision", None) or os.environ.get("P3P_PRECISION", "fp16")).lower()
         if self.precision not in P3P_PRECISION:
             raise ValueError(f"p3p_precision must be one of {sorted(P3P_PRECISION)}")
         self.out_dtype = torch.float32
         self._ws: Optional[torch.Tensor] = None
         self._blobs = {}
+        self._fp16_check = (None, False)
         self._dense_offsets = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -163,11 +164,45 @@ class PointPillarsEncoder(nn.Module):
             self._ws = torch.empty(max(need, 1), dtype=torch.uint8, device=device)
         return self._ws
 
-    def _blob(self, device, precision: str) -> torch.Tensor:
+    def _pfn_tensors(self):
         l0, l1 = self.voxel_encoder.pfn_layers[0], self.voxel_encoder.pfn_layers[1]
-        tensors = [l0.linear.weight, l0.norm.weight, l0.norm.bias, l0.norm.running_mean, l0.norm.running_var,
-                   l1.linear.weight, l1.norm.weight, l1.norm.bias, l1.norm.running_mean, l1.norm.running_var]
-        stamp = tuple((t._version, t.data_ptr()) for t in tensors) + (self.center_alias,)
+        return [l0.linear.weight, l0.norm.weight, l0.norm.bias, l0.norm.running_mean, l0.norm.running_var,
+                l1.linear.weight, l1.norm.weight, l1.norm.bias, l1.norm.running_mean, l1.norm.running_var]
+
+    def _stamp(self):
+        return tuple((t._version, t.data_ptr()) for t in self._pfn_tensors()) + (self.center_alias,)
+
+    @torch.no_grad()
+    def _fp16_safe(self) -> bool:
+        """P3P_PRECISION_FP16 feeds the second linear fp16 operands: safe while every layer-0 activation and folded
+        weight stays well inside the fp16 range.  |h_k| <= sum_i |a0_k W0[k, i]| * R + |b0_k| with R the largest
+        decorated coordinate magnitude (the grid extent).  One host sync, cached per weight version."""
+        stamp = self._stamp()
+        if self._fp16_check[0] == stamp:
+            return self._fp16_check[1]
+        w0, g0, be0, mu0, var0, w1, g1, _, _, var1 = [t.detach().float() for t in self._pfn_tensors()]
+        eps = float(self.voxel_encoder.pfn_layers[0].norm.eps)
+        a0 = g0 / torch.sqrt(var0 + eps)
+        a1 = g1 / torch.sqrt(var1 + eps)
+        R = max(abs(v) for v in self.point_cloud_range) + max(self.voxel_size)
+        h_bound = ((a0.abs().unsqueeze(1) * w0.abs()).sum(1) * R + (be0 - mu0 * a0).abs()).max()
+        w_bound = (a1.abs().unsqueeze(1) * w1.abs()).max()
+        ok = bool(torch.isfinite(h_bound) and torch.isfinite(w_bound) and h_bound < 3.0e4 and w_bound < 3.0e4)
+        self._fp16_check = (stamp, ok)
+        if not ok:
+            self.logger.warning("PFN activations may leave the fp16 range (bound %.3g): using tf32 operands", float(h_bound))
+        return ok
+
+    def _resolve_precision(self, precision: Optional[str]) -> str:
+        precision = precision or self.precision
+        if precision == "fp16" and not self._fp16_safe():
+            return "tf32"
+        return precision
+
+    def _blob(self, device, precision: str) -> torch.Tensor:
+        l0 = self.voxel_encoder.pfn_layers[0]
+        tensors = self._pfn_tensors()
+        stamp = self._stamp()
         hit = self._blobs.get((precision, device))
         if hit is not None and hit[0] == stamp:
             return hit[1]
@@ -192,7 +227,7 @@ class PointPillarsEncoder(nn.Module):
                     lidar_zero: bool = False, precision: Optional[str] = None) -> torch.Tensor:
         """voxelize -> PFN -> scatter, written into `out` (NLC (B, ny*nx, C) or NCHW channels [c_offset, c_offset+C))."""
         values, offsets, B = self._pack(x_lidar)
-        precision = precision or self.precision
+        precision = self._resolve_precision(precision)
         device = values.device
         grid = self._grid()
         total = values.shape[0]
@@ -256,7 +291,7 @@ class PointPillarsEncoder(nn.Module):
         """((V, C) pillar features in voxel order, coors (V, 4)) -- voxelize + PillarFeatureNet, before the scatter."""
         r = self.voxelize_raw(x_lidar, want_points=False)
         grid, B, total, device = r["_ctx"]
-        precision = precision or self.precision
+        precision = self._resolve_precision(precision)
         V = grid.max_voxels
         feats = torch.zeros(B, V, self.channels, dtype=torch.float32, device=device)
         with torch.cuda.device(device):

@@ -32,7 +32,7 @@ from .encoder import PointPillarsEncoder, _get
 class PatchEmbed(nn.Module):
     """timm.layers.PatchEmbed as the reference uses it (`flatten = False`, norm = Identity, NCHW output)."""
 
-    def __init__(self, img_size=224, patch_size=8, in_chans=3, embed_dim=384, bias=True, precision: str = "tf32"):
+    def __init__(self, img_size=224, patch_size=8, in_chans=3, embed_dim=384, bias=True, precision: str = "fp16"):
         super().__init__()
         self.img_size, self.patch_size, self.in_chans, self.embed_dim = int(img_size), int(patch_size), int(in_chans), int(embed_dim)
         self.flatten = False
@@ -102,7 +102,7 @@ class EarlyFusionFrontEnd(nn.Module):
         """Eval-mode fused path: both halves written in place into `out` (B, 2C, ny, nx); returns `out`."""
         dim = self.channels
         lidar_zero = self._dropout_now() if lidar_zero is None else bool(lidar_zero)
-        self.image_embed.forward_into(x_image, out, 2 * dim, 0, precision=self.lidar_embed.precision)
+        self.image_embed.forward_into(x_image, out, 2 * dim, 0)
         self.lidar_embed.encode_into(x_lidar, out, P3P_LAYOUT_NCHW, c_total=2 * dim, c_offset=dim, lidar_zero=lidar_zero)
         return out
 

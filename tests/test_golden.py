@@ -77,7 +77,7 @@ def test_cuda_path_reproduces_golden(cuda_device, name):
     assert np.array_equal(raw["pillar_coords"].cpu()[mask].numpy(), z["coors"])
     assert np.array_equal(raw["pillar_num_points"].cpu()[mask].numpy(), z["num_points"])
     assert np.array_equal(raw["pillar_point_idx"].cpu()[mask].numpy(), z["dense_idx"])
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", "tf32", "fp16"):
         feats, coors = enc.pillar_features(x, precision=prec)
         scale = max(float(np.abs(z["pillar_features"]).max()), 1e-6) if z["pillar_features"].size else 1.0
         assert np.abs(feats.cpu().numpy() - z["pillar_features"]).max(initial=0.0) <= TOL * scale, (name, prec)
@@ -100,7 +100,7 @@ def test_cuda_patch_embed_reproduces_golden(cuda_device):
     pe = PatchEmbed(224, 8, 3, C).to(cuda_device).eval()
     pe.load_state_dict(po.synth_weights(int(z["weight_seed"]), feat_channels=(64, C))[1])
     scale = float(np.abs(z["out"]).max())
-    for prec, tol in (("fp32", 1e-5), ("tf32", 1e-3), ("bf16", 1e-2)):
+    for prec, tol in (("fp32", 1e-5), ("tf32", 1e-3), ("fp16", 1e-3), ("bf16", 1e-2)):
         pe.precision = prec
         out = pe(img.to(cuda_device)).cpu().numpy()
         assert np.abs(out - z["out"]).max() <= tol * scale, prec

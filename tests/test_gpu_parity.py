@@ -14,7 +14,7 @@ from pixelspointspolygons_b200 import PointPillarsEncoder, default_cfg
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-4, "tf32": 1e-3, "bf16": 1e-2}
+TOL = {"fp32": 1e-4, "tf32": 1e-3, "fp16": 1e-3, "bf16": 1e-2}
 
 
 def build(dev, grid: po.GridSpec, seed=0, C=384):
@@ -79,7 +79,7 @@ def test_voxelizer_is_bit_exact_on_edge_cases(cuda_device, name):
         assert raw["num_pillars"].cpu().tolist() == counts, name
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "fp16", "bf16"])
 @pytest.mark.parametrize("name", ["occupancy_M", "z100_overwrites_cell", "ragged_batch", "empty_tile_between", "demo_shaped",
                                   "stability_shuffled", "x224_then_alias", "only_empty_tiles", "vmax_cut"])
 def test_features_and_canvas_match_oracle(cuda_device, name, prec):
@@ -220,6 +220,7 @@ def build_fusion(dev, seed=0, lidar_dropout=None, precision="tf32"):
 
     cfg = default_cfg(device=str(dev), lidar_dropout=lidar_dropout, p3p_precision=precision)
     fe = EarlyFusionFrontEnd(cfg).to(dev).eval()
+    fe.image_embed.precision = precision
     sd, sdi = po.synth_weights(seed)
     fe.lidar_embed.load_state_dict(sd)
     fe.image_embed.load_state_dict(sdi)
@@ -230,7 +231,7 @@ def build_fusion(dev, seed=0, lidar_dropout=None, precision="tf32"):
     return fe, ref_i, ref_l
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "fp16", "bf16"])
 def test_patch_embed_matches_conv2d(cuda_device, prec):
     fe, ref_i, _ = build_fusion(cuda_device, seed=12, precision=prec)
     g = torch.Generator().manual_seed(5)
@@ -266,7 +267,7 @@ def test_patch_embed_other_shapes_take_the_exact_route(cuda_device):
         assert_close(pe(img.to(cuda_device)), r, 1e-3, f"patch embed {size}/{patch}/{chans}/{dim}")
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32", "fp16", "bf16"])
 def test_early_fusion_concat_matches_oracle(cuda_device, prec):
     fe, ref_i, ref_l = build_fusion(cuda_device, seed=13, precision=prec)
     tiles = [po.synth_tile(20000, 41), po.synth_tile(500, 42, clustered=True), np.zeros((0, 3), np.float32)]
@@ -302,3 +303,19 @@ def test_sharded_batch_equals_single_gpu_batch(cuda_device):
         for world in (2, 4, 8):
             parts = [enc(shard.shard_lidar(x, r, world), return_flattened=False) for r in range(world)]
             assert torch.equal(torch.cat(parts, 0), whole), world
+
+
+def test_fp16_range_guard_falls_back_to_tf32(cuda_device):
+    """fp16 operands are only used while the layer-0 activations provably stay inside the fp16 range."""
+    enc, ref = build(cuda_device, po.GridSpec(), seed=15)
+    enc.precision = "fp16"
+    assert enc._resolve_precision(None) == "fp16"
+    tiles = [po.synth_tile(4000, 9)]
+    with torch.no_grad():
+        enc.voxel_encoder.pfn_layers[0].linear.weight.mul_(400.0)
+        ref.voxel_encoder.pfn_layers[0].linear.weight.mul_(400.0)
+        assert enc._resolve_precision(None) == "tf32"
+        out = enc(to_nested(tiles, cuda_device))
+        r = ref(tiles)
+    assert torch.isfinite(out).all()
+    assert_close(out, r, 1e-3, "fp16 guard -> tf32")
