@@ -317,8 +317,8 @@ struct TcCfg {
     static constexpr int kKSteps = kTf32 ? 4 : 2;         // UMMA_K = 8 (tf32) / 16 (16-bit): 32 bytes per step
     static constexpr int kNS = kTf32 ? 4 : 8;             // B-operand stages: pillar pairs in flight
     static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * kHStage + 2 * (size_t)kGStage;
-    static constexpr size_t kSmemFloats = 10 * 32 + 384 + kNF * 64 * 4;
-    static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + (2 * kNS + 16) * 8 + 16;
+    static constexpr size_t kSmemFloats = 10 * 32 + 384 + kNF * 128 * 4;
+    static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + (2 * kNS + 24) * 8 + 16;
 };
 
 __device__ __forceinline__ float max32(const float (&v)[32]) {
@@ -348,15 +348,14 @@ __device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) {
         asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
 }
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
-    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
+// 16-byte global -> shared copy, zero-filled when src_bytes == 0
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16_wait(uint32_t taddr, float (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -367,16 +366,10 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t taddr, float (&v)[16]) {
         : "memory");
 }
 
-// item -> (tile, position inside the tile) for the 8 items of a unit with ONE 32-bit division
+// (tile, position inside the tile) of a unit's first item
 struct UnitLoc {
     int b0, r0;  // of the unit's first item
 };
-__device__ __forceinline__ UnitLoc locate_unit(const PfnArgs& a, int item0) {
-    UnitLoc u;
-    u.b0 = item0 / a.items_per_tile;
-    u.r0 = item0 - u.b0 * a.items_per_tile;
-    return u;
-}
 // validity bits of the 8 items of a unit (bit i: item0 + i holds a pillar)
 __device__ __forceinline__ unsigned unit_valid_mask(const PfnArgs& a, int item0, const UnitLoc& u) {
     unsigned vmask = 0;
@@ -408,6 +401,20 @@ __device__ __forceinline__ unsigned unit_valid_mask(const PfnArgs& a, int item0,
     return vmask;
 }
 
+// running (tile, position) of an item index that advances by a fixed stride: one division at start-up, none afterwards
+struct ItemWalk {
+    int b, r, db, dr, ipt;
+    __device__ __forceinline__ void init(int item, int delta, int items_per_tile) {
+        ipt = items_per_tile;
+        b = item / ipt; r = item - b * ipt;
+        db = delta / ipt; dr = delta - db * ipt;
+    }
+    __device__ __forceinline__ void step() {
+        b += db; r += dr;
+        if (r >= ipt) { r -= ipt; ++b; }
+    }
+};
+
 template <int kPrec>
 __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     using Cfg = TcCfg<kPrec>;
@@ -422,13 +429,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     unsigned char* sG = sH + kNS * Cfg::kHStage;                        // [2 batch slots][16 rows]
     float* sFront = reinterpret_cast<float*>(sG + 2 * Cfg::kGStage);    // [10][32]
     float* sB1 = sFront + 10 * 32;                                      // [384]
-    float4* sPts = reinterpret_cast<float4*>(sB1 + 384);                // [kNF][64] centred points of the pillar in work
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sPts + kNF * 64);
+    float4* sPts = reinterpret_cast<float4*>(sB1 + 384);                // [kNF][2][64] points of the pillar in work / of the next one
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPts + kNF * 128);
     uint64_t* h_full = bars;                  // [kNS] front end -> MMA (2 arrivals: the two warps of a pair)
     uint64_t* h_empty = bars + kNS;           // [kNS] MMA -> front end (tcgen05.commit)
-    uint64_t* t_full = bars + 2 * kNS;        // [3]   MMA -> epilogue group m (tcgen05.commit), per pair
-    uint64_t* t_empty = t_full + 3;           // [3]   epilogue group m -> MMA (128 arrivals)
-    uint64_t* gt_full = t_empty + 3;          // [3]   MMA -> epilogue group m, per batch (G accumulator)
+    uint64_t* t_full = bars + 2 * kNS;        // [3][2] MMA -> epilogue group m (tcgen05.commit), per pillar of a pair
+    uint64_t* t_empty = t_full + 6;           // [3][2] epilogue group m -> MMA (128 arrivals)
+    uint64_t* gt_full = t_empty + 6;          // [3]   MMA -> epilogue group m, per batch (G accumulator)
     uint64_t* gt_empty = gt_full + 3;         // [3]   epilogue group m -> MMA (128 arrivals)
     uint64_t* g_empty = gt_empty + 3;         // [2]   MMA -> front end: hmax rows of the batch slot consumed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_empty + 2);
@@ -444,10 +451,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
         for (int i = 0; i < kNS; ++i) { mbar_init(&h_full[i], 2); mbar_init(&h_empty[i], 1); }
-        for (int i = 0; i < 3; ++i) {
-            mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128);
-            mbar_init(&gt_full[i], 1); mbar_init(&gt_empty[i], 128);
-        }
+        for (int i = 0; i < 6; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&gt_full[i], 1); mbar_init(&gt_empty[i], 128); }
         mbar_init(&g_empty[0], 1); mbar_init(&g_empty[1], 1);
         fence_mbar_init();
     }
@@ -474,9 +479,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     if (warp == 0) {
         // =========================== MMA issuer ===========================
         // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers);
-        // one elected lane issues the tcgen05 instructions and their commits.
+        // one elected lane issues the tcgen05 instructions and their commits.  A pair's accumulator tile is issued
+        // as its two pillars (N = 64 each) with their own full / empty barriers, so the MMA of the next pair's first
+        // pillar runs while the epilogue still reads the second pillar of this one.
         const bool leader = elect_one();
-        const uint32_t idesc_main = make_idesc(Cfg::kFmt, 128, 128);
+        const uint32_t idesc_half = make_idesc(Cfg::kFmt, 128, 64);
         const uint32_t idesc_g = make_idesc(Cfg::kFmt, 128, 16);
         const uint32_t desc_hi = (Cfg::kSBO >> 4) | (1u << 14) | (Cfg::kLayout << 29);
         const uint32_t a1_lo = (smem_u32(sA1) >> 4) | (1u << 16), a2_lo = (smem_u32(sA2) >> 4) | (1u << 16);
@@ -489,20 +496,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             tc_fence_after();
             const uint32_t hs_lo = h_lo + (uint32_t)st * (Cfg::kHStage >> 4);
 #pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                if (m < MT) {
-                    mbar_wait(&t_empty[m], ((uint32_t)p & 1) ^ 1);
-                    PTL(0, p, 1 + m);
-                    tc_fence_after();
-                    if (leader) {
-                        const uint32_t d_main = tmem_base + m * kTmemStage;
+            for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-                        for (int k = 0; k < Cfg::kKSteps; ++k)
-                            tc_mma<kTf32>(d_main, ((uint64_t)desc_hi << 32) | (a1_lo + (uint32_t)((m * Cfg::kATile + k * 32) >> 4)),
-                                          ((uint64_t)desc_hi << 32) | (hs_lo + (uint32_t)(k * 2)), idesc_main, k > 0);
-                        tc_commit(&t_full[m]);
+                for (int m = 0; m < 3; ++m) {
+                    if (m < MT) {
+                        mbar_wait(&t_empty[m * 2 + hf], ((uint32_t)p & 1) ^ 1);
+                        if (hf == 0) PTL(0, p, 1 + m);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t d_main = tmem_base + m * kTmemStage + hf * 64;
+#pragma unroll
+                            for (int k = 0; k < Cfg::kKSteps; ++k)
+                                tc_mma<kTf32>(d_main, ((uint64_t)desc_hi << 32) | (a1_lo + (uint32_t)((m * Cfg::kATile + k * 32) >> 4)),
+                                              ((uint64_t)desc_hi << 32) | (hs_lo + (uint32_t)((hf * 64 * Cfg::RB) >> 4) + (uint32_t)(k * 2)),
+                                              idesc_half, k > 0);
+                            tc_commit(&t_full[m * 2 + hf]);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
             if (leader) tc_commit(&h_empty[st]);
@@ -534,49 +545,73 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         }
     } else if (warp < kEpiWarp0) {
         // =========================== front end: warp fw takes item fw of every unit ===========================
-        // lane = (channel pair cp, point parity par): 32 steps over the pillar's 64 slots, 2 channels x 1 point per lane
-        // and step; the point comes from shared memory (broadcast), the channel constants sit in registers.
+        // lane = (channel octet o, point pt): 8 independent combos per lane, combo i = slot pt + 8 i of the pillar x the
+        // lane's 8 channels (one 16-byte chunk of a 16-bit operand row, two chunks of a tf32 row).  The pillar's points
+        // arrive by cp.async (zero-filled beyond n) into a per-warp double buffer one item ahead, its descriptor word is
+        // loaded two items ahead and only decoded one iteration later; the channel constants of layer 0 sit in registers.
         const int fw = warp - 1, half = fw & 1, pr = fw >> 1;
-        const int cp = lane & 15, par = lane >> 4;
-        auto cst = [&](int row) { return *reinterpret_cast<const float2*>(sFront + row * 32 + 2 * cp); };
-        const float2 ux = cst(0), uy = cst(1), uz = cst(2), kcx = cst(3), kcy = cst(4), wmx = cst(5), wmy = cst(6), wmz = cst(7),
-                     b0v = cst(8), hpv = cst(9);
-        float4* pts = sPts + fw * 64;
-        const uint32_t pts_sa = smem_u32(pts) + (uint32_t)par * 16u;
-        // byte offset of this lane's channel pair inside an operand row, per swizzle phase of the row
-        uint32_t uoff[4];
-        uint32_t hpad16 = 0;
+        const int o = lane & 3, pt = lane >> 2;
+        float2 ux[4], uy[4], uz[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ux[i] = *reinterpret_cast<const float2*>(sFront + 0 * 32 + 8 * o + 2 * i);
+            uy[i] = *reinterpret_cast<const float2*>(sFront + 1 * 32 + 8 * o + 2 * i);
+            uz[i] = *reinterpret_cast<const float2*>(sFront + 2 * 32 + 8 * o + 2 * i);
+        }
+        const float* kc = sFront + 8 * o;  // rows 3..9 of the lane's 8 channels
+        float4* pbuf = sPts + fw * 128;    // [2][64]
+        const uint32_t pbuf_sa = smem_u32(pbuf);
+        // byte offset of the lane's first slot inside a stage: row (half * 64 + pt), the lane's chunk(s) under the swizzle
+        uint32_t row_off[2];
         if constexpr (kTf32) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) uoff[j] = (uint32_t)((((cp >> 1) ^ ((j << 1) | par)) * 16) + (cp & 1) * 8);
+            row_off[0] = (uint32_t)(half * 64 + pt) * Cfg::RB + (uint32_t)(((2 * o) ^ pt) * 16);
+            row_off[1] = (uint32_t)(half * 64 + pt) * Cfg::RB + (uint32_t)(((2 * o + 1) ^ pt) * 16);
         } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) uoff[j] = (uint32_t)((((cp >> 2) ^ j) * 16) + (cp & 3) * 4);
-            hpad16 = pack_relu16<kPrec>(hpv.x, hpv.y);
+            row_off[0] = (uint32_t)(half * 64 + pt) * Cfg::RB + (uint32_t)((o ^ ((pt >> 1) & 3)) * 16);
+            row_off[1] = 0;
         }
-        const uint32_t hrow0 = (uint32_t)(half * 64 + par) * Cfg::RB;  // row of step 0 inside a stage
-
+        const bool canvas = (a.item_mode == kItemsCanvas);
+        const float inv_nx = 1.0f / (float)a.g.nx;
+        const int delta = (int)gridDim.x * kUnit;
         auto item_of = [&](int j) -> int { return (j < my_units) ? ((int)blockIdx.x + j * (int)gridDim.x) * kUnit + fw : total_items; };
-        // software pipeline: descriptor two ahead, points one ahead
-        Item it_cur = fetch_item(a, item_of(0));
-        Item it_nxt = fetch_item(a, item_of(1));
-        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-        if (it_cur.valid) {
-            const float4* sl = item_slots(a, it_cur);
-            if (lane < it_cur.n) c0 = sl[lane];
-            if (lane + 32 < it_cur.n) c1 = sl[lane + 32];
-        }
+        // raw descriptor word of item j (canvas: cell_desc; list: resolved when decoded); no branch depends on the load
+        auto load_desc = [&](int j) -> int {
+            const int item = item_of(j);
+            return (canvas && item < total_items) ? __ldg(a.ws.cell_desc + item) : -1;
+        };
+        auto decode = [&](int j, int d, const ItemWalk& wk) -> Item {
+            if (!canvas) return fetch_item(a, item_of(j));
+            Item it;
+            it.valid = d >= 0 ? 1 : 0;
+            it.b = wk.b; it.cell = wk.r;
+            it.key = d & 0xFFFF; it.n = d >> 16;
+            const int cy = __float2int_rz(((float)wk.r + 0.5f) * inv_nx), cx = wk.r - cy * a.g.nx;
+            it.ctr_x = __fmaf_rn((float)cx, a.g.vx, a.g.x_off);
+            it.ctr_y = __fmaf_rn((float)cy, a.g.vy, a.g.y_off);
+            return it;
+        };
+        auto prefetch_points = [&](const Item& it, int buf) {
+            if (it.valid) {
+                const float4* sl = item_slots(a, it);
+                const uint32_t dst = pbuf_sa + (uint32_t)buf * 1024u + (uint32_t)lane * 16u;
+                cp_async16(dst, sl + lane, lane < it.n ? 16u : 0u);
+                cp_async16(dst + 512u, sl + lane + 32, lane + 32 < it.n ? 16u : 0u);
+            }
+        };
+        ItemWalk wk;  // position of the item decoded next
+        wk.init(item_of(0) < total_items ? item_of(0) : 0, delta, a.items_per_tile);
+        Item it_cur = decode(0, load_desc(0), wk);
+        wk.step();
+        int d_nxt = load_desc(1);
+        prefetch_points(it_cur, 0);
         for (int j = 0; j < my_units; ++j) {
             const Item it = it_cur;
-            const float4 p0 = c0, p1 = c1;
-            it_cur = it_nxt;
-            c0 = make_float4(0.f, 0.f, 0.f, 0.f); c1 = c0;
-            if (it_cur.valid) {
-                const float4* sl = item_slots(a, it_cur);
-                if (lane < it_cur.n) c0 = sl[lane];
-                if (lane + 32 < it_cur.n) c1 = sl[lane + 32];
-            }
-            it_nxt = fetch_item(a, item_of(j + 2));
+            cp_async_wait_all();
+            __syncwarp();  // points of item j visible to every lane; every lane is done with the other buffer
+            it_cur = decode(j + 1, d_nxt, wk);
+            wk.step();
+            prefetch_points(it_cur, (j + 1) & 1);
+            d_nxt = load_desc(j + 2);
 
             const int p = j * kPairsPerUnit + pr, st = p % kNS;
             const uint32_t use = (uint32_t)(p / kNS), bt = (uint32_t)j / kBatchUnits, slot = bt & 1u;
@@ -587,55 +622,131 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             PTL(1 + fw, j, 1);
             if (it.valid) {
                 const int n = it.n;
-                float mean3[3];
+                const float4* P = pbuf + (j & 1) * 64;
+                // cluster mean on the fixed-point grid (exact integer sums: independent of the order); lane c < 3 turns
+                // the sums of coordinate c into the mean
+                float mean_o;
                 {
-                    const float c0v[3] = {p0.x, p0.y, p0.z}, c1v[3] = {p1.x, p1.y, p1.z};
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {  // padded lanes hold zeros
-                        int l0, h0, l1, h1;
-                        fix_split(c0v[i], a.g.fix_scale, l0, h0);
-                        fix_split(c1v[i], a.g.fix_scale, l1, h1);
-                        mean3[i] = fix_mean(__reduce_add_sync(0xffffffffu, l0 + l1), __reduce_add_sync(0xffffffffu, h0 + h1),
-                                            a.g.fix_inv, (float)n);
-                    }
+                    const float4 s0 = P[lane], s1 = P[lane + 32];
+                    int lo0, hi0, lo1, hi1, sl[3], sh[3];
+                    fix_split(s0.x, a.g.fix_scale, lo0, hi0); fix_split(s1.x, a.g.fix_scale, lo1, hi1);
+                    sl[0] = __reduce_add_sync(0xffffffffu, lo0 + lo1); sh[0] = __reduce_add_sync(0xffffffffu, hi0 + hi1);
+                    fix_split(s0.y, a.g.fix_scale, lo0, hi0); fix_split(s1.y, a.g.fix_scale, lo1, hi1);
+                    sl[1] = __reduce_add_sync(0xffffffffu, lo0 + lo1); sh[1] = __reduce_add_sync(0xffffffffu, hi0 + hi1);
+                    fix_split(s0.z, a.g.fix_scale, lo0, hi0); fix_split(s1.z, a.g.fix_scale, lo1, hi1);
+                    sl[2] = __reduce_add_sync(0xffffffffu, lo0 + lo1); sh[2] = __reduce_add_sync(0xffffffffu, hi0 + hi1);
+                    const int msl = (o == 0) ? sl[0] : ((o == 1) ? sl[1] : sl[2]);
+                    const int msh = (o == 0) ? sh[0] : ((o == 1) ? sh[1] : sh[2]);
+                    mean_o = fix_mean(msl, msh, a.g.fix_inv, (float)n);
                 }
-                const float mpx = mean3[0] - it.ctr_x, mpy = mean3[1] - it.ctr_y, mz = mean3[2];
-                float2 kap;
-                kap.x = __fmaf_rn(-wmz.x, mz, __fmaf_rn(-wmy.x, mpy, __fmaf_rn(-wmx.x, mpx, __fmaf_rn(kcy.x, it.ctr_y, __fmaf_rn(kcx.x, it.ctr_x, b0v.x)))));
-                kap.y = __fmaf_rn(-wmz.y, mz, __fmaf_rn(-wmy.y, mpy, __fmaf_rn(-wmx.y, mpx, __fmaf_rn(kcy.y, it.ctr_y, __fmaf_rn(kcx.y, it.ctr_x, b0v.y)))));
-                pts[lane] = make_float4(p0.x - it.ctr_x, p0.y - it.ctr_y, p0.z, 0.f);
-                pts[lane + 32] = make_float4(p1.x - it.ctr_x, p1.y - it.ctr_y, p1.z, 0.f);
-                __syncwarp();
-                const uint32_t hst_sa = smem_u32(sH) + (uint32_t)st * Cfg::kHStage + hrow0;
+                float qx[8], qy[8], qz[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 q = P[pt + 8 * i];
+                    qx[i] = q.x - it.ctr_x; qy[i] = q.y - it.ctr_y; qz[i] = q.z;
+                }
+                const float mpx = __shfl_sync(0xffffffffu, mean_o, 0) - it.ctr_x;
+                const float mpy = __shfl_sync(0xffffffffu, mean_o, 1) - it.ctr_y;
+                const float mz = __shfl_sync(0xffffffffu, mean_o, 2);
+                float2 kap[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 kcx = *reinterpret_cast<const float2*>(kc + 3 * 32 + 2 * i), kcy = *reinterpret_cast<const float2*>(kc + 4 * 32 + 2 * i);
+                    const float2 wmx = *reinterpret_cast<const float2*>(kc + 5 * 32 + 2 * i), wmy = *reinterpret_cast<const float2*>(kc + 6 * 32 + 2 * i);
+                    const float2 wmz = *reinterpret_cast<const float2*>(kc + 7 * 32 + 2 * i), b0v = *reinterpret_cast<const float2*>(kc + 8 * 32 + 2 * i);
+                    float2 t = ffma2(kcx, make_float2(it.ctr_x, it.ctr_x), b0v);
+                    t = ffma2(kcy, make_float2(it.ctr_y, it.ctr_y), t);
+                    t = ffma2(wmx, make_float2(-mpx, -mpx), t);
+                    t = ffma2(wmy, make_float2(-mpy, -mpy), t);
+                    kap[i] = ffma2(wmz, make_float2(-mz, -mz), t);
+                }
+                const uint32_t hst_sa = smem_u32(sH) + (uint32_t)st * Cfg::kHStage;
                 const uint32_t g_sa = smem_u32(sG) + slot * Cfg::kGStage + (uint32_t)grow * Cfg::RB;
                 if constexpr (kTf32) {
-                    float m0 = 0.f, m1 = 0.f;
+                    float mx8[8];
 #pragma unroll
-                    for (int s = 0; s < 32; ++s) {
-                        const float4 q = lds128(pts_sa + (uint32_t)s * 32u);
-                        const float2 v = ffma2(ux, make_float2(q.x, q.x), ffma2(uy, make_float2(q.y, q.y), ffma2(uz, make_float2(q.z, q.z), kap)));
-                        float h0 = fmaxf(v.x, 0.f), h1 = fmaxf(v.y, 0.f);
-                        if (n < 64 && 2 * s + par >= n) { h0 = hpv.x; h1 = hpv.y; }  // padded slots carry relu(BN(0))
-                        m0 = fmaxf(m0, h0); m1 = fmaxf(m1, h1);
+                    for (int c = 0; c < 8; ++c) mx8[c] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float h[8];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float2 v = ffma2(ux[c], make_float2(qx[i], qx[i]), ffma2(uy[c], make_float2(qy[i], qy[i]), ffma2(uz[c], make_float2(qz[i], qz[i]), kap[c])));
+                            h[2 * c] = fmaxf(v.x, 0.f); h[2 * c + 1] = fmaxf(v.y, 0.f);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(mx8[c], h[c]);
                         // operands are already scaled by (1 + 2^-12): the MMA's truncation rounds them to nearest tf32
-                        sts64(hst_sa + (uint32_t)s * (2u * Cfg::RB) + uoff[s & 3], h0, h1);
+                        sts128(hst_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), __float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]), __float_as_uint(h[3]));
+                        sts128(hst_sa + row_off[1] + (uint32_t)i * (8u * Cfg::RB), __float_as_uint(h[4]), __float_as_uint(h[5]), __float_as_uint(h[6]), __float_as_uint(h[7]));
                     }
-                    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 16));
-                    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 16));
-                    if (par == 0) sts64(g_sa + (uint32_t)((((cp >> 1) ^ (grow & 7)) * 16) + (cp & 1) * 8), m0, m1);
-                } else {
-                    uint32_t mm = 0;
+                    if (n < 64) {  // (warp-uniform) padded slots carry relu(BN(0)); the zero-filled points above computed relu(kappa)
+                        float hp[8];
 #pragma unroll
-                    for (int s = 0; s < 32; ++s) {
-                        const float4 q = lds128(pts_sa + (uint32_t)s * 32u);
-                        const float2 v = ffma2(ux, make_float2(q.x, q.x), ffma2(uy, make_float2(q.y, q.y), ffma2(uz, make_float2(q.z, q.z), kap)));
-                        uint32_t h = pack_relu16<kPrec>(v.x, v.y);
-                        if (n < 64 && 2 * s + par >= n) h = hpad16;
-                        mm = max16x2<kPrec>(mm, h);
-                        sts32(hst_sa + (uint32_t)s * (2u * Cfg::RB) + uoff[s & 3], h);
+                        for (int c = 0; c < 8; ++c) hp[c] = kc[9 * 32 + c];
+                        // the kept slots' maximum has to be redone without the padded ones
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) mx8[c] = hp[c];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (pt + 8 * i >= n) {
+                                sts128(hst_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), __float_as_uint(hp[0]), __float_as_uint(hp[1]), __float_as_uint(hp[2]), __float_as_uint(hp[3]));
+                                sts128(hst_sa + row_off[1] + (uint32_t)i * (8u * Cfg::RB), __float_as_uint(hp[4]), __float_as_uint(hp[5]), __float_as_uint(hp[6]), __float_as_uint(hp[7]));
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    const float2 v = ffma2(ux[c], make_float2(qx[i], qx[i]), ffma2(uy[c], make_float2(qy[i], qy[i]), ffma2(uz[c], make_float2(qz[i], qz[i]), kap[c])));
+                                    mx8[2 * c] = fmaxf(mx8[2 * c], v.x); mx8[2 * c + 1] = fmaxf(mx8[2 * c + 1], v.y);
+                                }
+                            }
+                        }
                     }
-                    mm = max16x2<kPrec>(mm, __shfl_xor_sync(0xffffffffu, mm, 16));
-                    if (par == 0) sts32(g_sa + (uint32_t)((((cp >> 2) ^ ((grow >> 1) & 3)) * 16) + (cp & 3) * 4), mm);
+#pragma unroll
+                    for (int off = 4; off < 32; off <<= 1) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(mx8[c], __shfl_xor_sync(0xffffffffu, mx8[c], off));
+                    }
+                    if (pt == 0) {
+                        sts128(g_sa + (uint32_t)(((2 * o) ^ (grow & 7)) * 16), __float_as_uint(mx8[0]), __float_as_uint(mx8[1]), __float_as_uint(mx8[2]), __float_as_uint(mx8[3]));
+                        sts128(g_sa + (uint32_t)(((2 * o + 1) ^ (grow & 7)) * 16), __float_as_uint(mx8[4]), __float_as_uint(mx8[5]), __float_as_uint(mx8[6]), __float_as_uint(mx8[7]));
+                    }
+                } else {
+                    uint32_t mm[4] = {0u, 0u, 0u, 0u};
+                    if (n == 64) {  // (warp-uniform) full pillar: no padded slots
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            uint32_t h[4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float2 v = ffma2(ux[c], make_float2(qx[i], qx[i]), ffma2(uy[c], make_float2(qy[i], qy[i]), ffma2(uz[c], make_float2(qz[i], qz[i]), kap[c])));
+                                h[c] = pack_relu16<kPrec>(v.x, v.y);
+                                mm[c] = max16x2<kPrec>(mm[c], h[c]);
+                            }
+                            sts128(hst_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), h[0], h[1], h[2], h[3]);
+                        }
+                    } else {
+                        uint32_t hp[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) hp[c] = pack_relu16<kPrec>(kc[9 * 32 + 2 * c], kc[9 * 32 + 2 * c + 1]);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            uint32_t h[4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float2 v = ffma2(ux[c], make_float2(qx[i], qx[i]), ffma2(uy[c], make_float2(qy[i], qy[i]), ffma2(uz[c], make_float2(qz[i], qz[i]), kap[c])));
+                                h[c] = pack_relu16<kPrec>(v.x, v.y);
+                                if (pt + 8 * i >= n) h[c] = hp[c];  // padded slots carry relu(BN(0))
+                                mm[c] = max16x2<kPrec>(mm[c], h[c]);
+                            }
+                            sts128(hst_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), h[0], h[1], h[2], h[3]);
+                        }
+                    }
+#pragma unroll
+                    for (int off = 4; off < 32; off <<= 1) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) mm[c] = max16x2<kPrec>(mm[c], __shfl_xor_sync(0xffffffffu, mm[c], off));
+                    }
+                    if (pt == 0) sts128(g_sa + (uint32_t)((o ^ ((grow >> 1) & 3)) * 16), mm[0], mm[1], mm[2], mm[3]);
                 }
             }
             fence_async_smem();
@@ -652,8 +763,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             const float b1c = sB1[c];
             const bool c_ok = c < a.bl.C;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(m * kTmemStage);
-            const bool nchw = (a.item_mode == kItemsCanvas) && (a.out_layout == P3P_LAYOUT_NCHW);
+            const bool canvas = (a.item_mode == kItemsCanvas);
+            const bool nchw = canvas && (a.out_layout == P3P_LAYOUT_NCHW);
             const bool nchw_vec = nchw && (a.items_per_tile % kUnit == 0);
+            const bool rows_f32 = !nchw && (a.out_dtype == P3P_DTYPE_F32);
+            const int C = a.bl.C;
+            ItemWalk wk;  // position of the first item of the next unit
+            wk.init((int)blockIdx.x * kUnit < total_items ? (int)blockIdx.x * kUnit : 0, (int)gridDim.x * kUnit, a.items_per_tile);
             uint32_t gp = 0, bt = 0;
             for (int j0 = 0; j0 < my_units; j0 += kBatchUnits, ++bt) {
                 const int nun = (my_units - j0 < kBatchUnits) ? my_units - j0 : kBatchUnits;
@@ -667,7 +783,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                     loc[uu].b0 = 0; loc[uu].r0 = 0;
                     vmask[uu] = 0;
                     if (uu < nun) {
-                        loc[uu] = locate_unit(a, item0[uu]);
+                        loc[uu].b0 = wk.b; loc[uu].r0 = wk.r;
+                        wk.step();
                         vmask[uu] = unit_valid_mask(a, item0[uu], loc[uu]);
                     }
                 }
@@ -676,23 +793,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                 for (int q = 0; q < kBatchPairs; ++q) {
                     rmax[2 * q] = 0.f; rmax[2 * q + 1] = 0.f;
                     if (q < nun * kPairsPerUnit) {  // warp-uniform
-                        if (quad == 0) PTL(9 + m, gp, 0);
-                        mbar_wait(&t_full[m], gp & 1);
-                        if (quad == 0) PTL(9 + m, gp, 1);
-                        tc_fence_after();
-                        float v[32];
-                        tmem_ld32_wait(taddr + 0, v);
-                        float mA = max32(v);
-                        tmem_ld32_wait(taddr + 32, v);
-                        mA = fmaxf(mA, max32(v));
-                        tmem_ld32_wait(taddr + 64, v);
-                        float mB = max32(v);
-                        tmem_ld32_wait(taddr + 96, v);
-                        mB = fmaxf(mB, max32(v));
-                        tc_fence_before();
-                        mbar_arrive(&t_empty[m]);
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            if (quad == 0 && hf == 0) PTL(9 + m, gp, 0);
+                            mbar_wait(&t_full[m * 2 + hf], gp & 1);
+                            if (quad == 0 && hf == 0) PTL(9 + m, gp, 1);
+                            tc_fence_after();
+                            float v[32];
+                            tmem_ld32_wait(taddr + hf * 64, v);
+                            float mx = max32(v);
+                            tmem_ld32_wait(taddr + hf * 64 + 32, v);
+                            mx = fmaxf(mx, max32(v));
+                            tc_fence_before();
+                            mbar_arrive(&t_empty[m * 2 + hf]);
+                            rmax[2 * q + hf] = mx;
+                        }
                         if (quad == 0) PTL(9 + m, gp, 2);
-                        rmax[2 * q] = mA; rmax[2 * q + 1] = mB;
                         ++gp;
                     }
                 }
@@ -709,8 +825,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                     if (uu >= nun) break;
                     float ob[kUnit];
 #pragma unroll
-                    for (int i = 0; i < kUnit; ++i)
-                        ob[i] = ((vmask[uu] >> i) & 1u) ? fmaxf(rmax[uu * kUnit + i] + g[uu * kUnit + i] + b1c, 0.f) : 0.f;
+                    for (int i = 0; i < kUnit; ++i) ob[i] = fmaxf(rmax[uu * kUnit + i] + (g[uu * kUnit + i] + b1c), 0.f);
+                    if (vmask[uu] != 0xFFu) {  // (warp-uniform) some items of the unit hold no pillar
+#pragma unroll
+                        for (int i = 0; i < kUnit; ++i)
+                            if (!((vmask[uu] >> i) & 1u)) ob[i] = 0.f;
+                    }
                     if (nchw_vec) {
                         const int64_t idx = ((int64_t)loc[uu].b0 * a.c_total + a.c_offset + c) * a.items_per_tile + loc[uu].r0;
                         if (a.out_dtype == P3P_DTYPE_F32) {
@@ -721,6 +841,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                             uint4* dst = reinterpret_cast<uint4*>(static_cast<unsigned short*>(a.out) + idx);
                             dst[0] = make_uint4(pack_bf16(ob[0], ob[1]), pack_bf16(ob[2], ob[3]), pack_bf16(ob[4], ob[5]), pack_bf16(ob[6], ob[7]));
                         }
+                    } else if (canvas && rows_f32 && item0[uu] + kUnit <= total_items) {
+                        // (B, ny nx, C) rows: a warp writes 32 consecutive channels of one cell, 8 cells C floats apart
+                        float* dst = static_cast<float*>(a.out) + (int64_t)item0[uu] * C + c;
+#pragma unroll
+                        for (int i = 0; i < kUnit; ++i) dst[(int64_t)i * C] = ob[i];
                     } else {
                         int b = loc[uu].b0, r = loc[uu].r0;
 #pragma unroll
@@ -728,9 +853,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                             const int item = item0[uu] + i;
                             const bool v = (vmask[uu] >> i) & 1u;
                             // list rows past num_pillars stay untouched; canvas cells are always written
-                            if (item < total_items && (v || a.item_mode == kItemsCanvas)) {
+                            if (item < total_items && (v || canvas)) {
                                 const int64_t idx = nchw ? ((int64_t)b * a.c_total + a.c_offset + c) * a.items_per_tile + r
-                                                         : (int64_t)item * a.bl.C + c;
+                                                         : (int64_t)item * C + c;
                                 store_scalar(a, idx, ob[i]);
                             }
                             if (++r == a.items_per_tile) { r = 0; ++b; }
