@@ -13,15 +13,7 @@
 //         = relu(max_p(W1a' h_p) + W1b' hmax + b1)  (relu and "+ const" are monotone; the BN scale is already
 //                                                    inside W1a', so its sign does not matter)
 //
-// pfn_tc_kernel (M == 64, C <= 384): per CTA a persistent pipeline
-//   4 front-end warps  : one pillar per warp at a time; layer 0 in its affine form
-//                        W0' d_p + b0 = Ux x' + Uy y' + Uz z + kappa(pillar)   (x' = x - centre_x, ...)
-//                        -> 3 FMA per (point, channel); rows written (tf32 / bf16) straight into the swizzled
-//                        K-major B-operand tile in shared memory; hmax via redux.sync.max.f32
-//   1 MMA thread       : per pillar pair and 128-channel tile: D[128 ch x 128 pts] = W1a' H^T and
-//                        D[128 ch x 16] = W1b' hmax^T, tcgen05.mma, accumulators in TMEM (3 stages)
-//   12 epilogue warps  : warp group m owns channel tile m: tcgen05.ld, max over the pillar's 64 columns with
-//                        3-input max, + G + b1, relu, then 32-byte NCHW sectors or coalesced NLC rows.
+// pfn_tc_kernel (M == 64, C <= 384): persistent warp-specialised pipeline, described at the kernel.
 // The decorated (V, M, 8) tensor and every (V, M, *) intermediate of the reference never exist in HBM.
 //
 // pfn_simt_kernel: exact fp32 FMA, literal 8-channel formulation, any M and C -- the GPU-side cross-check of the
@@ -296,13 +288,16 @@ __global__ void zero_lidar_kernel(PfnArgs a) {
 // tensor-core kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kNF = 8;                         // front-end warps: warp w takes item w of every unit
-constexpr int kEpiWarp0 = 1 + kNF;             // warp 0: TMEM alloc + MMA issue; 1..kNF: front end; then 12 epilogue warps
-constexpr int kTcThreads = 32 * (kEpiWarp0 + 12);
-constexpr int kUnit = 8;                       // items per unit (one 32-byte NCHW sector per channel) = 4 pillar pairs
+constexpr int kMmaWarps = 3;                   // warp m < 3: MMA issue for channel tile m (warp 0 also owns the TMEM allocation)
+constexpr int kEpiWarp0 = kMmaWarps + kNF;     // then kNF front-end warps, then the epilogue warps
+constexpr int kEpiGroups = 3;                  // epilogue groups of 4 warps (one warp per TMEM lane quarter)
+constexpr int kTcThreads = 32 * (kEpiWarp0 + 4 * kEpiGroups);
+constexpr int kUnit = 8;                       // items per unit = 4 pillar pairs, consecutive canvas cells
 constexpr int kPairsPerUnit = kUnit / 2;
-constexpr int kBatchUnits = 2;                 // units per G batch: one N = 16 MMA gives W1b' hmax for 16 items
-constexpr int kBatchPairs = kBatchUnits * kPairsPerUnit;
-constexpr int kTmemStage = 144;                // TMEM columns per channel tile: 128 (pair) + 16 (G of a batch)
+constexpr int kTmemStage = 144;                // TMEM columns per accumulator stage: 128 (pillar pair) + 16 (W1b' hmax of the pair)
+constexpr int kTmemStages = 3;                 // ring of accumulator stages shared by the epilogue groups
+constexpr int kValidRing = 64;               // pairs of validity flags in flight between front end and epilogue (>= kNS + ring slack)
+constexpr int kStageRows = 144;                // operand rows of a pair: 2 x 64 slots + the 2 hmax rows (padded to 16)
 
 template <int kPrec>
 struct TcCfg {
@@ -310,24 +305,16 @@ struct TcCfg {
     static constexpr int kFmt = kTf32 ? 2 : (kPrec == P3P_PRECISION_BF16 ? 1 : 0);  // UMMA operand format code
     static constexpr int RB = kTf32 ? 128 : 64;           // bytes of one K = 32 operand row
     static constexpr int kATile = 128 * RB;               // 128 channels
-    static constexpr int kHStage = 128 * RB;              // 2 pillars x 64 rows
-    static constexpr int kGStage = 16 * RB;               // hmax rows of the 16 items of a batch
+    static constexpr int kHStage = kStageRows * RB;       // 2 pillars x 64 rows + 16 hmax rows
     static constexpr uint32_t kLayout = kTf32 ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
     static constexpr uint32_t kSBO = 8 * RB;
     static constexpr int kKSteps = kTf32 ? 4 : 2;         // UMMA_K = 8 (tf32) / 16 (16-bit): 32 bytes per step
     static constexpr int kNS = kTf32 ? 4 : 8;             // B-operand stages: pillar pairs in flight
-    static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * kHStage + 2 * (size_t)kGStage;
+    static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * kHStage;
     static constexpr size_t kSmemFloats = 10 * 32 + 384 + kNF * 128 * 4;
-    static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + (2 * kNS + 24) * 8 + 16;
+    static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + (2 * kNS + 2 * kTmemStages + 2) * 8 + 16 + 2 * kNF * 4 + 2 * kValidRing;
 };
 
-__device__ __forceinline__ float max32(const float (&v)[32]) {
-    float r[11];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) r[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-    r[10] = fmaxf(v[30], v[31]);
-    return fmaxf(fmax3(fmax3(r[0], r[1], r[2]), fmax3(r[3], r[4], r[5]), fmax3(r[6], r[7], r[8])), fmaxf(r[9], r[10]));
-}
 
 // two fp32 -> packed 16-bit pair with relu fused into the conversion (lo = first channel)
 template <int kPrec>
@@ -355,55 +342,14 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16_wait(uint32_t taddr, float (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-        "tcgen05.wait::ld.sync.aligned;\n"
-        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
-          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
 
-// (tile, position inside the tile) of a unit's first item
-struct UnitLoc {
-    int b0, r0;  // of the unit's first item
-};
-// validity bits of the 8 items of a unit (bit i: item0 + i holds a pillar)
-__device__ __forceinline__ unsigned unit_valid_mask(const PfnArgs& a, int item0, const UnitLoc& u) {
-    unsigned vmask = 0;
-    const int total = (int)a.num_items;
-    if (a.item_mode == kItemsCanvas) {
-        if (item0 + kUnit <= total) {  // item0 is a multiple of 8: two aligned 16-byte loads
-            const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.ws.cell_desc + item0));
-            const int4 d1 = __ldg(reinterpret_cast<const int4*>(a.ws.cell_desc + item0) + 1);
-            vmask = (d0.x >= 0 ? 1u : 0u) | (d0.y >= 0 ? 2u : 0u) | (d0.z >= 0 ? 4u : 0u) | (d0.w >= 0 ? 8u : 0u) |
-                    (d1.x >= 0 ? 16u : 0u) | (d1.y >= 0 ? 32u : 0u) | (d1.z >= 0 ? 64u : 0u) | (d1.w >= 0 ? 128u : 0u);
-        } else {
-#pragma unroll
-            for (int i = 0; i < kUnit; ++i)
-                if (item0 + i < total && __ldg(a.ws.cell_desc + item0 + i) >= 0) vmask |= 1u << i;
-        }
-    } else {
-        int b = u.b0, r = u.r0;
-        int np = (item0 < total) ? a.ws.num_pil[b] : 0;
-#pragma unroll
-        for (int i = 0; i < kUnit; ++i) {
-            if (item0 + i < total && r < np) vmask |= 1u << i;
-            if (++r == a.items_per_tile) {
-                r = 0;
-                ++b;
-                np = (item0 + i + 1 < total) ? a.ws.num_pil[b] : 0;
-            }
-        }
-    }
-    return vmask;
-}
-
-// running (tile, position) of an item index that advances by a fixed stride: one division at start-up, none afterwards
+// running (tile, position) of an item index that advances by a fixed stride: divisions at start-up only
 struct ItemWalk {
-    int b, r, db, dr, ipt;
+    int b, r, ipt, db, dr;
     __device__ __forceinline__ void init(int item, int delta, int items_per_tile) {
         ipt = items_per_tile;
         b = item / ipt; r = item - b * ipt;
@@ -415,6 +361,23 @@ struct ItemWalk {
     }
 };
 
+__device__ __forceinline__ float max32(const float (&v)[32]) {
+    float r[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) r[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    r[10] = fmaxf(v[30], v[31]);
+    return fmaxf(fmax3(fmax3(r[0], r[1], r[2]), fmax3(r[3], r[4], r[5]), fmax3(r[6], r[7], r[8])), fmaxf(r[9], r[10]));
+}
+
+// pfn_tc_kernel (M == 64, C <= 384): per CTA a persistent pipeline
+//   8 front-end warps  : warp w takes item w of every unit (8 consecutive items); layer 0 in its affine form
+//                        W0' d_p + b0 = Ux x' + Uy y' + Uz z + kappa(pillar)   (x' = x - centre_x, ...)
+//                        -> 3 FMA per (point, channel); 16-byte row chunks written (tf32 / 16-bit) straight into the
+//                        swizzled K-major B-operand stage of the pair, hmax into the stage's two extra rows
+//   3 MMA warps        : warp m, per pair: D[128 ch x 2 x 64 pts] = W1a'[tile m] H^T and D[128 ch x 16] = W1b'[tile m] hmax^T
+//                        into accumulator stage m (one elected thread issues)
+//   3 x 4 epilogue warps: group g reads accumulator stage g: tcgen05.ld, max over each
+//                        pillar's 64 columns with 3-input max, + W1b' hmax + b1, relu, store of the two cells.
 template <int kPrec>
 __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     using Cfg = TcCfg<kPrec>;
@@ -425,20 +388,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     unsigned char* base = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
     unsigned char* sA1 = base;
     unsigned char* sA2 = sA1 + 3 * Cfg::kATile;
-    unsigned char* sH = sA2 + 3 * Cfg::kATile;
-    unsigned char* sG = sH + kNS * Cfg::kHStage;                        // [2 batch slots][16 rows]
-    float* sFront = reinterpret_cast<float*>(sG + 2 * Cfg::kGStage);    // [10][32]
+    unsigned char* sH = sA2 + 3 * Cfg::kATile;                          // [kNS][144 rows]
+    float* sFront = reinterpret_cast<float*>(sH + kNS * Cfg::kHStage);  // [10][32]
     float* sB1 = sFront + 10 * 32;                                      // [384]
-    float4* sPts = reinterpret_cast<float4*>(sB1 + 384);                // [kNF][2][64] points of the pillar in work / of the next one
+    float4* sPts = reinterpret_cast<float4*>(sB1 + 384);                // [kNF][2 sets][64] points of the pillar in work / of the next one
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPts + kNF * 128);
     uint64_t* h_full = bars;                  // [kNS] front end -> MMA (2 arrivals: the two warps of a pair)
-    uint64_t* h_empty = bars + kNS;           // [kNS] MMA -> front end (tcgen05.commit)
-    uint64_t* t_full = bars + 2 * kNS;        // [3][2] MMA -> epilogue group m (tcgen05.commit), per pillar of a pair
-    uint64_t* t_empty = t_full + 6;           // [3][2] epilogue group m -> MMA (128 arrivals)
-    uint64_t* gt_full = t_empty + 6;          // [3]   MMA -> epilogue group m, per batch (G accumulator)
-    uint64_t* gt_empty = gt_full + 3;         // [3]   epilogue group m -> MMA (128 arrivals)
-    uint64_t* g_empty = gt_empty + 3;         // [2]   MMA -> front end: hmax rows of the batch slot consumed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_empty + 2);
+    uint64_t* h_empty = bars + kNS;           // [kNS] MMA -> front end (one tcgen05.commit per channel tile)
+    uint64_t* t_full = bars + 2 * kNS;        // [3] MMA warp m -> epilogue group m (tcgen05.commit), per pair
+    uint64_t* t_empty = t_full + kTmemStages; // [3] epilogue group m -> MMA warp m (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + kTmemStages);
+    int* sDesc = reinterpret_cast<int*>(tmem_slot + 2);                 // [kNF][2] descriptor word of the item decoded next
+    unsigned char* sValid = reinterpret_cast<unsigned char*>(sDesc + 2 * kNF);  // [kValidRing pairs][2]: the item holds a pillar
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int MT = a.bl.MT;
@@ -446,14 +407,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     const int num_units = (total_items + kUnit - 1) / kUnit;
     const int my_units = (num_units > (int)blockIdx.x) ? (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int my_pairs = my_units * kPairsPerUnit;  // pairs this CTA processes, in order p = 0, 1, ...
+    const bool canvas = (a.item_mode == kItemsCanvas);
 
     // ---- one-time setup --------------------------------------------------------------------------
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
-        for (int i = 0; i < kNS; ++i) { mbar_init(&h_full[i], 2); mbar_init(&h_empty[i], 1); }
-        for (int i = 0; i < 6; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
-        for (int i = 0; i < 3; ++i) { mbar_init(&gt_full[i], 1); mbar_init(&gt_empty[i], 128); }
-        mbar_init(&g_empty[0], 1); mbar_init(&g_empty[1], 1);
+        for (int i = 0; i < kNS; ++i) { mbar_init(&h_full[i], 2); mbar_init(&h_empty[i], (uint32_t)MT); }
+        for (int i = 0; i < kTmemStages; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
         fence_mbar_init();
     }
     {
@@ -464,7 +424,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             reinterpret_cast<uint4*>(sA1)[i] = g1[i];
             reinterpret_cast<uint4*>(sA2)[i] = g2[i];
         }
-        for (int i = tid; i < 2 * Cfg::kGStage / 16; i += kTcThreads) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0, 0, 0, 0);
+        // the 14 unused hmax rows of every stage feed accumulator columns nobody reads; zero them once all the same
+        for (int i = tid; i < kNS * 16 * Cfg::RB / 16; i += kTcThreads) {
+            const int st = i / (16 * Cfg::RB / 16), o = i - st * (16 * Cfg::RB / 16);
+            reinterpret_cast<uint4*>(sH + (size_t)st * Cfg::kHStage + 128 * Cfg::RB)[o] = make_uint4(0, 0, 0, 0);
+        }
         const float* fg = reinterpret_cast<const float*>(a.blob + a.bl.off_front);
         const float* b1g = reinterpret_cast<const float*>(a.blob + a.bl.off_b1);
         for (int i = tid; i < 10 * 32; i += kTcThreads) sFront[i] = fg[i];
@@ -476,80 +440,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // =========================== MMA issuer ===========================
-        // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers);
-        // one elected lane issues the tcgen05 instructions and their commits.  A pair's accumulator tile is issued
-        // as its two pillars (N = 64 each) with their own full / empty barriers, so the MMA of the next pair's first
-        // pillar runs while the epilogue still reads the second pillar of this one.
-        const bool leader = elect_one();
-        const uint32_t idesc_half = make_idesc(Cfg::kFmt, 128, 64);
-        const uint32_t idesc_g = make_idesc(Cfg::kFmt, 128, 16);
-        const uint32_t desc_hi = (Cfg::kSBO >> 4) | (1u << 14) | (Cfg::kLayout << 29);
-        const uint32_t a1_lo = (smem_u32(sA1) >> 4) | (1u << 16), a2_lo = (smem_u32(sA2) >> 4) | (1u << 16);
-        const uint32_t h_lo = (smem_u32(sH) >> 4) | (1u << 16), g_lo = (smem_u32(sG) >> 4) | (1u << 16);
-        int st = 0;
-        uint32_t use = 0;
-        for (int p = 0; p < my_pairs; ++p) {
-            mbar_wait(&h_full[st], use & 1);
-            PTL(0, p, 0);
-            tc_fence_after();
-            const uint32_t hs_lo = h_lo + (uint32_t)st * (Cfg::kHStage >> 4);
+    if (warp < kMmaWarps) {
+        // =========================== MMA issuers: warp m owns channel tile m and accumulator stage m ===========================
+        // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers); one elected
+        // lane issues the tcgen05 instructions and their commits.  One issuing warp per tile keeps the per-pair chain of
+        // barrier waits (about 100 cycles each, even when already satisfied) short.
+        const int m = warp;
+        if (m < MT) {
+            const bool leader = elect_one();
+            const uint32_t idesc_main = make_idesc(Cfg::kFmt, 128, 128);
+            const uint32_t idesc_g = make_idesc(Cfg::kFmt, 128, 16);
+            const uint32_t desc_hi = (Cfg::kSBO >> 4) | (1u << 14) | (Cfg::kLayout << 29);
+            const uint32_t a1_lo = ((smem_u32(sA1) + (uint32_t)(m * Cfg::kATile)) >> 4) | (1u << 16);
+            const uint32_t a2_lo = ((smem_u32(sA2) + (uint32_t)(m * Cfg::kATile)) >> 4) | (1u << 16);
+            const uint32_t h_lo = (smem_u32(sH) >> 4) | (1u << 16);
+            const uint32_t d_main = tmem_base + (uint32_t)(m * kTmemStage);
+            int st = 0;
+            uint32_t use = 0;
+            for (int p = 0; p < my_pairs; ++p) {
+                mbar_wait(&h_full[st], use & 1);
+                if (m == 0) PTL(0, p, 0);
+                tc_fence_after();
+                const uint32_t hs_lo = h_lo + (uint32_t)st * (Cfg::kHStage >> 4);
+                const uint32_t gs_lo = hs_lo + (uint32_t)((128 * Cfg::RB) >> 4);
+                {
+                    mbar_wait(&t_empty[m], ((uint32_t)p & 1u) ^ 1u);
+                    if (m == 0) PTL(0, p, 1);
+                    tc_fence_after();
+                    if (leader) {
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
+                        for (int k = 0; k < Cfg::kKSteps; ++k)
+                            tc_mma<kTf32>(d_main, ((uint64_t)desc_hi << 32) | (a1_lo + (uint32_t)(k * 2)),
+                                          ((uint64_t)desc_hi << 32) | (hs_lo + (uint32_t)(k * 2)), idesc_main, k > 0);
 #pragma unroll
-                for (int m = 0; m < 3; ++m) {
-                    if (m < MT) {
-                        mbar_wait(&t_empty[m * 2 + hf], ((uint32_t)p & 1) ^ 1);
-                        if (hf == 0) PTL(0, p, 1 + m);
-                        tc_fence_after();
-                        if (leader) {
-                            const uint32_t d_main = tmem_base + m * kTmemStage + hf * 64;
-#pragma unroll
-                            for (int k = 0; k < Cfg::kKSteps; ++k)
-                                tc_mma<kTf32>(d_main, ((uint64_t)desc_hi << 32) | (a1_lo + (uint32_t)((m * Cfg::kATile + k * 32) >> 4)),
-                                              ((uint64_t)desc_hi << 32) | (hs_lo + (uint32_t)((hf * 64 * Cfg::RB) >> 4) + (uint32_t)(k * 2)),
-                                              idesc_half, k > 0);
-                            tc_commit(&t_full[m * 2 + hf]);
-                        }
-                        __syncwarp();
+                        for (int k = 0; k < Cfg::kKSteps; ++k)
+                            tc_mma<kTf32>(d_main + 128, ((uint64_t)desc_hi << 32) | (a2_lo + (uint32_t)(k * 2)),
+                                          ((uint64_t)desc_hi << 32) | (gs_lo + (uint32_t)(k * 2)), idesc_g, k > 0);
+                        tc_commit(&t_full[m]);
                     }
+                    __syncwarp();
                 }
-            }
-            if (leader) tc_commit(&h_empty[st]);
-            __syncwarp();
-            if (++st == kNS) { st = 0; ++use; }
-            // ---- end of a batch (16 items): G = W1b' hmax for all of them with one N = 16 MMA chain per channel tile ----
-            if ((p & (kBatchPairs - 1)) == kBatchPairs - 1 || p == my_pairs - 1) {
-                const uint32_t bt = (uint32_t)p / kBatchPairs, slot = bt & 1u;
-                const uint32_t gs_lo = g_lo + slot * (Cfg::kGStage >> 4);
-#pragma unroll
-                for (int m = 0; m < 3; ++m) {
-                    if (m < MT) {
-                        mbar_wait(&gt_empty[m], (bt & 1u) ^ 1u);
-                        tc_fence_after();
-                        if (leader) {
-                            const uint32_t d_g = tmem_base + m * kTmemStage + 128;
-#pragma unroll
-                            for (int k = 0; k < Cfg::kKSteps; ++k)
-                                tc_mma<kTf32>(d_g, ((uint64_t)desc_hi << 32) | (a2_lo + (uint32_t)((m * Cfg::kATile + k * 32) >> 4)),
-                                              ((uint64_t)desc_hi << 32) | (gs_lo + (uint32_t)(k * 2)), idesc_g, k > 0);
-                            tc_commit(&gt_full[m]);
-                        }
-                        __syncwarp();
-                    }
-                }
-                if (leader) tc_commit(&g_empty[slot]);
+                if (leader) tc_commit(&h_empty[st]);
                 __syncwarp();
+                if (m == 0) PTL(0, p, 2);
+                if (++st == kNS) { st = 0; ++use; }
             }
         }
     } else if (warp < kEpiWarp0) {
         // =========================== front end: warp fw takes item fw of every unit ===========================
         // lane = (channel octet o, point pt): 8 independent combos per lane, combo i = slot pt + 8 i of the pillar x the
         // lane's 8 channels (one 16-byte chunk of a 16-bit operand row, two chunks of a tf32 row).  The pillar's points
-        // arrive by cp.async (zero-filled beyond n) into a per-warp double buffer one item ahead, its descriptor word is
-        // loaded two items ahead and only decoded one iteration later; the channel constants of layer 0 sit in registers.
-        const int fw = warp - 1, half = fw & 1, pr = fw >> 1;
+        // arrive by cp.async (zero-filled beyond n) into a per-warp double buffer one item ahead; the descriptor word is
+        // loaded two items ahead and decoded one iteration later; the channel constants of layer 0 sit in registers.
+        const int fw = warp - kMmaWarps, half = fw & 1, pr = fw >> 1;
         const int o = lane & 3, pt = lane >> 2;
         float2 ux[4], uy[4], uz[4];
 #pragma unroll
@@ -559,7 +502,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             uz[i] = *reinterpret_cast<const float2*>(sFront + 2 * 32 + 8 * o + 2 * i);
         }
         const float* kc = sFront + 8 * o;  // rows 3..9 of the lane's 8 channels
-        float4* pbuf = sPts + fw * 128;    // [2][64]
+        float4* pbuf = sPts + fw * 128;    // [2 sets][64]
         const uint32_t pbuf_sa = smem_u32(pbuf);
         // byte offset of the lane's first slot inside a stage: row (half * 64 + pt), the lane's chunk(s) under the swizzle
         uint32_t row_off[2];
@@ -570,55 +513,67 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             row_off[0] = (uint32_t)(half * 64 + pt) * Cfg::RB + (uint32_t)((o ^ ((pt >> 1) & 3)) * 16);
             row_off[1] = 0;
         }
-        const bool canvas = (a.item_mode == kItemsCanvas);
+        // hmax row (128 + half) of the stage: swizzle phase (row >> 1) & 3 = 0 (16-bit rows), row & 7 = half (tf32 rows)
+        const uint32_t g_off0 = (uint32_t)(128 + half) * Cfg::RB + (uint32_t)(kTf32 ? (((2 * o) ^ half) * 16) : (o * 16));
+        const uint32_t g_off1 = (uint32_t)(128 + half) * Cfg::RB + (uint32_t)(((2 * o + 1) ^ half) * 16);
         const float inv_nx = 1.0f / (float)a.g.nx;
-        const int delta = (int)gridDim.x * kUnit;
         auto item_of = [&](int j) -> int { return (j < my_units) ? ((int)blockIdx.x + j * (int)gridDim.x) * kUnit + fw : total_items; };
-        // raw descriptor word of item j (canvas: cell_desc; list: resolved when decoded); no branch depends on the load
-        auto load_desc = [&](int j) -> int {
+        // descriptor word of item j (canvas: cell_desc; list: resolved when decoded) travels through shared memory by
+        // cp.async like the points, so no register waits on a global load
+        int* my_desc = sDesc + 2 * fw;
+        const uint32_t my_desc_sa = smem_u32(my_desc);
+        auto prefetch_desc = [&](int j) {
             const int item = item_of(j);
-            return (canvas && item < total_items) ? __ldg(a.ws.cell_desc + item) : -1;
+            if (lane == 0) {
+                if (canvas && item < total_items) cp_async4(my_desc_sa + 4u * (uint32_t)(j & 1), a.ws.cell_desc + item);
+                else my_desc[j & 1] = -1;
+            }
         };
-        auto decode = [&](int j, int d, const ItemWalk& wk) -> Item {
-            if (!canvas) return fetch_item(a, item_of(j));
+        ItemWalk wk;  // position of the item decoded next
+        wk.init(item_of(0) < total_items ? item_of(0) : 0, (int)gridDim.x * kUnit, a.items_per_tile);
+        auto decode = [&](int j, int d) -> Item {
             Item it;
-            it.valid = d >= 0 ? 1 : 0;
-            it.b = wk.b; it.cell = wk.r;
-            it.key = d & 0xFFFF; it.n = d >> 16;
-            const int cy = __float2int_rz(((float)wk.r + 0.5f) * inv_nx), cx = wk.r - cy * a.g.nx;
-            it.ctr_x = __fmaf_rn((float)cx, a.g.vx, a.g.x_off);
-            it.ctr_y = __fmaf_rn((float)cy, a.g.vy, a.g.y_off);
+            if (!canvas) {
+                it = fetch_item(a, item_of(j));
+            } else {
+                it.valid = d >= 0 ? 1 : 0;
+                it.b = wk.b; it.cell = wk.r;
+                it.key = d & 0xFFFF; it.n = d >> 16;
+                const int cy = __float2int_rz(((float)wk.r + 0.5f) * inv_nx), cx = wk.r - cy * a.g.nx;
+                it.ctr_x = __fmaf_rn((float)cx, a.g.vx, a.g.x_off);
+                it.ctr_y = __fmaf_rn((float)cy, a.g.vy, a.g.y_off);
+            }
+            wk.step();
             return it;
         };
-        auto prefetch_points = [&](const Item& it, int buf) {
+        auto prefetch_points = [&](const Item& it, int set) {
             if (it.valid) {
                 const float4* sl = item_slots(a, it);
-                const uint32_t dst = pbuf_sa + (uint32_t)buf * 1024u + (uint32_t)lane * 16u;
+                const uint32_t dst = pbuf_sa + (uint32_t)set * 1024u + (uint32_t)lane * 16u;
                 cp_async16(dst, sl + lane, lane < it.n ? 16u : 0u);
                 cp_async16(dst + 512u, sl + lane + 32, lane + 32 < it.n ? 16u : 0u);
             }
         };
-        ItemWalk wk;  // position of the item decoded next
-        wk.init(item_of(0) < total_items ? item_of(0) : 0, delta, a.items_per_tile);
-        Item it_cur = decode(0, load_desc(0), wk);
-        wk.step();
-        int d_nxt = load_desc(1);
+        prefetch_desc(0);
+        cp_async_wait_all();
+        __syncwarp();
+        Item it_cur = decode(0, my_desc[0]);
+        __syncwarp();
         prefetch_points(it_cur, 0);
+        prefetch_desc(1);
         for (int j = 0; j < my_units; ++j) {
             const Item it = it_cur;
             cp_async_wait_all();
-            __syncwarp();  // points of item j visible to every lane; every lane is done with the other buffer
-            it_cur = decode(j + 1, d_nxt, wk);
-            wk.step();
+            __syncwarp();  // points of item j and descriptor of item j + 1 visible to every lane; the other buffers are free
+            it_cur = decode(j + 1, my_desc[(j + 1) & 1]);
+            __syncwarp();
             prefetch_points(it_cur, (j + 1) & 1);
-            d_nxt = load_desc(j + 2);
+            prefetch_desc(j + 2);
 
             const int p = j * kPairsPerUnit + pr, st = p % kNS;
-            const uint32_t use = (uint32_t)(p / kNS), bt = (uint32_t)j / kBatchUnits, slot = bt & 1u;
-            const int grow = ((j & (kBatchUnits - 1)) * kPairsPerUnit + pr) * 2 + half;  // row of this item in the batch's G operand
+            const uint32_t use = (uint32_t)(p / kNS);
             PTL(1 + fw, j, 0);
             mbar_wait(&h_empty[st], (use & 1u) ^ 1u);
-            mbar_wait(&g_empty[slot], ((bt >> 1) & 1u) ^ 1u);
             PTL(1 + fw, j, 1);
             if (it.valid) {
                 const int n = it.n;
@@ -660,12 +615,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                     t = ffma2(wmy, make_float2(-mpy, -mpy), t);
                     kap[i] = ffma2(wmz, make_float2(-mz, -mz), t);
                 }
-                const uint32_t hst_sa = smem_u32(sH) + (uint32_t)st * Cfg::kHStage;
-                const uint32_t g_sa = smem_u32(sG) + slot * Cfg::kGStage + (uint32_t)grow * Cfg::RB;
+                const uint32_t stage_sa = smem_u32(sH) + (uint32_t)st * Cfg::kHStage;
                 if constexpr (kTf32) {
-                    float mx8[8];
+                    float hp[8], mx8[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) mx8[c] = 0.f;
+                    for (int c = 0; c < 8; ++c) { hp[c] = kc[9 * 32 + c]; mx8[c] = (n < 64) ? hp[c] : 0.f; }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         float h[8];
@@ -674,32 +628,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                             const float2 v = ffma2(ux[c], make_float2(qx[i], qx[i]), ffma2(uy[c], make_float2(qy[i], qy[i]), ffma2(uz[c], make_float2(qz[i], qz[i]), kap[c])));
                             h[2 * c] = fmaxf(v.x, 0.f); h[2 * c + 1] = fmaxf(v.y, 0.f);
                         }
+                        if (pt + 8 * i >= n) {  // padded slots carry relu(BN(0))
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) h[c] = hp[c];
+                        }
 #pragma unroll
                         for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(mx8[c], h[c]);
                         // operands are already scaled by (1 + 2^-12): the MMA's truncation rounds them to nearest tf32
-                        sts128(hst_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), __float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]), __float_as_uint(h[3]));
-                        sts128(hst_sa + row_off[1] + (uint32_t)i * (8u * Cfg::RB), __float_as_uint(h[4]), __float_as_uint(h[5]), __float_as_uint(h[6]), __float_as_uint(h[7]));
-                    }
-                    if (n < 64) {  // (warp-uniform) padded slots carry relu(BN(0)); the zero-filled points above computed relu(kappa)
-                        float hp[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) hp[c] = kc[9 * 32 + c];
-                        // the kept slots' maximum has to be redone without the padded ones
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) mx8[c] = hp[c];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (pt + 8 * i >= n) {
-                                sts128(hst_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), __float_as_uint(hp[0]), __float_as_uint(hp[1]), __float_as_uint(hp[2]), __float_as_uint(hp[3]));
-                                sts128(hst_sa + row_off[1] + (uint32_t)i * (8u * Cfg::RB), __float_as_uint(hp[4]), __float_as_uint(hp[5]), __float_as_uint(hp[6]), __float_as_uint(hp[7]));
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < 4; ++c) {
-                                    const float2 v = ffma2(ux[c], make_float2(qx[i], qx[i]), ffma2(uy[c], make_float2(qy[i], qy[i]), ffma2(uz[c], make_float2(qz[i], qz[i]), kap[c])));
-                                    mx8[2 * c] = fmaxf(mx8[2 * c], v.x); mx8[2 * c + 1] = fmaxf(mx8[2 * c + 1], v.y);
-                                }
-                            }
-                        }
+                        sts128(stage_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), __float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]), __float_as_uint(h[3]));
+                        sts128(stage_sa + row_off[1] + (uint32_t)i * (8u * Cfg::RB), __float_as_uint(h[4]), __float_as_uint(h[5]), __float_as_uint(h[6]), __float_as_uint(h[7]));
                     }
 #pragma unroll
                     for (int off = 4; off < 32; off <<= 1) {
@@ -707,8 +644,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                         for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(mx8[c], __shfl_xor_sync(0xffffffffu, mx8[c], off));
                     }
                     if (pt == 0) {
-                        sts128(g_sa + (uint32_t)(((2 * o) ^ (grow & 7)) * 16), __float_as_uint(mx8[0]), __float_as_uint(mx8[1]), __float_as_uint(mx8[2]), __float_as_uint(mx8[3]));
-                        sts128(g_sa + (uint32_t)(((2 * o + 1) ^ (grow & 7)) * 16), __float_as_uint(mx8[4]), __float_as_uint(mx8[5]), __float_as_uint(mx8[6]), __float_as_uint(mx8[7]));
+                        sts128(stage_sa + g_off0, __float_as_uint(mx8[0]), __float_as_uint(mx8[1]), __float_as_uint(mx8[2]), __float_as_uint(mx8[3]));
+                        sts128(stage_sa + g_off1, __float_as_uint(mx8[4]), __float_as_uint(mx8[5]), __float_as_uint(mx8[6]), __float_as_uint(mx8[7]));
                     }
                 } else {
                     uint32_t mm[4] = {0u, 0u, 0u, 0u};
@@ -722,7 +659,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                                 h[c] = pack_relu16<kPrec>(v.x, v.y);
                                 mm[c] = max16x2<kPrec>(mm[c], h[c]);
                             }
-                            sts128(hst_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), h[0], h[1], h[2], h[3]);
+                            sts128(stage_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), h[0], h[1], h[2], h[3]);
                         }
                     } else {
                         uint32_t hp[4];
@@ -738,7 +675,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                                 if (pt + 8 * i >= n) h[c] = hp[c];  // padded slots carry relu(BN(0))
                                 mm[c] = max16x2<kPrec>(mm[c], h[c]);
                             }
-                            sts128(hst_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), h[0], h[1], h[2], h[3]);
+                            sts128(stage_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), h[0], h[1], h[2], h[3]);
                         }
                     }
 #pragma unroll
@@ -746,122 +683,103 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) mm[c] = max16x2<kPrec>(mm[c], __shfl_xor_sync(0xffffffffu, mm[c], off));
                     }
-                    if (pt == 0) sts128(g_sa + (uint32_t)((o ^ ((grow >> 1) & 3)) * 16), mm[0], mm[1], mm[2], mm[3]);
+                    if (pt == 0) sts128(stage_sa + g_off0, mm[0], mm[1], mm[2], mm[3]);
                 }
             }
+            if (lane == 0) sValid[(p & (kValidRing - 1)) * 2 + half] = (unsigned char)it.valid;
             fence_async_smem();
             __syncwarp();
             PTL(1 + fw, j, 2);
             if (lane == 0) mbar_arrive(&h_full[st]);
         }
     } else {
-        // =========================== epilogue: warp group m owns channel tile m ===========================
-        const int m = (warp - kEpiWarp0) >> 2;
+        // =========================== epilogue: group g owns channel tile g ===========================
+        const int g = (warp - kEpiWarp0) >> 2;
         const int quad = warp & 3;  // TMEM lanes this warp may read: 32 * (warp id % 4)
-        const int c = m * 128 + quad * 32 + lane;
-        if (m < MT) {
-            const float b1c = sB1[c];
-            const bool c_ok = c < a.bl.C;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(m * kTmemStage);
-            const bool canvas = (a.item_mode == kItemsCanvas);
-            const bool nchw = canvas && (a.out_layout == P3P_LAYOUT_NCHW);
-            const bool nchw_vec = nchw && (a.items_per_tile % kUnit == 0);
-            const bool rows_f32 = !nchw && (a.out_dtype == P3P_DTYPE_F32);
-            const int C = a.bl.C;
-            ItemWalk wk;  // position of the first item of the next unit
-            wk.init((int)blockIdx.x * kUnit < total_items ? (int)blockIdx.x * kUnit : 0, (int)gridDim.x * kUnit, a.items_per_tile);
-            uint32_t gp = 0, bt = 0;
-            for (int j0 = 0; j0 < my_units; j0 += kBatchUnits, ++bt) {
-                const int nun = (my_units - j0 < kBatchUnits) ? my_units - j0 : kBatchUnits;
-                // where the batch's units go and which of their items exist (loads in flight during the pair loop)
-                int item0[kBatchUnits];
-                UnitLoc loc[kBatchUnits];
-                unsigned vmask[kBatchUnits];
+        const bool nchw = canvas && (a.out_layout == P3P_LAYOUT_NCHW);
+        const bool f32 = (a.out_dtype == P3P_DTYPE_F32);
+        const int C = a.bl.C, ipt = a.items_per_tile;
+        // fast path: whole units inside one tile, every item exists -> no per-item bounds, two-cell vector stores
+        const bool fast = canvas && (total_items % kUnit == 0) && (ipt % kUnit == 0);  // (the front end marks items beyond the end invalid)
+        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int cl = quad * 32 + lane;  // channel inside a 128-channel tile
+        float b1v[3];
 #pragma unroll
-                for (int uu = 0; uu < kBatchUnits; ++uu) {
-                    item0[uu] = ((int)blockIdx.x + (j0 + uu) * (int)gridDim.x) * kUnit;
-                    loc[uu].b0 = 0; loc[uu].r0 = 0;
-                    vmask[uu] = 0;
-                    if (uu < nun) {
-                        loc[uu].b0 = wk.b; loc[uu].r0 = wk.r;
-                        wk.step();
-                        vmask[uu] = unit_valid_mask(a, item0[uu], loc[uu]);
-                    }
-                }
-                float rmax[kBatchUnits * kUnit];
-#pragma unroll
-                for (int q = 0; q < kBatchPairs; ++q) {
-                    rmax[2 * q] = 0.f; rmax[2 * q + 1] = 0.f;
-                    if (q < nun * kPairsPerUnit) {  // warp-uniform
-#pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            if (quad == 0 && hf == 0) PTL(9 + m, gp, 0);
-                            mbar_wait(&t_full[m * 2 + hf], gp & 1);
-                            if (quad == 0 && hf == 0) PTL(9 + m, gp, 1);
-                            tc_fence_after();
-                            float v[32];
-                            tmem_ld32_wait(taddr + hf * 64, v);
-                            float mx = max32(v);
-                            tmem_ld32_wait(taddr + hf * 64 + 32, v);
-                            mx = fmaxf(mx, max32(v));
-                            tc_fence_before();
-                            mbar_arrive(&t_empty[m * 2 + hf]);
-                            rmax[2 * q + hf] = mx;
-                        }
-                        if (quad == 0) PTL(9 + m, gp, 2);
-                        ++gp;
-                    }
-                }
-                float g[16];
-                mbar_wait(&gt_full[m], bt & 1);
+        for (int mm = 0; mm < 3; ++mm) b1v[mm] = sB1[mm * 128 + cl];
+        ItemWalk wu;  // position of the first item of the unit in work
+        wu.init((int)blockIdx.x * kUnit < total_items ? (int)blockIdx.x * kUnit : 0, (int)gridDim.x * kUnit, ipt);
+        int unit_item0 = (int)blockIdx.x * kUnit;
+        int jn = 0;
+        for (int p = 0; p < (g < MT ? my_pairs : 0); ++p) {
+            const int pr = p & (kPairsPerUnit - 1);
+            const int item = unit_item0 + 2 * pr;
+            const int ub = wu.b, ur = wu.r;  // tile / position of the unit's first item
+            if (pr == kPairsPerUnit - 1) { wu.step(); unit_item0 += (int)gridDim.x * kUnit; }
+            {
+                const int m = g;  // group g reads accumulator stage g = channel tile g
+                const uint32_t ts = (uint32_t)g;
+                const uint32_t tph = (uint32_t)p & 1u;
+                const uint32_t taddr = tlane + ts * kTmemStage;
+                float va[32], vb[32], g0, g1;
+                if (quad == 0) PTL(9 + g, jn, 0);
+                mbar_wait(&t_full[ts], tph);
+                if (quad == 0) PTL(9 + g, jn, 1);
                 tc_fence_after();
-                tmem_ld16_wait(taddr + 128, g);
+                tmem_ld32_wait(taddr, va);
+                tmem_ld32_wait(taddr + 32, vb);
+                tmem_ld2_wait(taddr + 128, g0, g1);
+                const float mA = fmaxf(max32(va), max32(vb));
+                tmem_ld32_wait(taddr + 64, va);
+                tmem_ld32_wait(taddr + 96, vb);
                 tc_fence_before();
-                mbar_arrive(&gt_empty[m]);
-                if (quad == 0) PTL(9 + m, gp - 1, 3);
-                if (!c_ok) continue;
-#pragma unroll
-                for (int uu = 0; uu < kBatchUnits; ++uu) {
-                    if (uu >= nun) break;
-                    float ob[kUnit];
-#pragma unroll
-                    for (int i = 0; i < kUnit; ++i) ob[i] = fmaxf(rmax[uu * kUnit + i] + (g[uu * kUnit + i] + b1c), 0.f);
-                    if (vmask[uu] != 0xFFu) {  // (warp-uniform) some items of the unit hold no pillar
-#pragma unroll
-                        for (int i = 0; i < kUnit; ++i)
-                            if (!((vmask[uu] >> i) & 1u)) ob[i] = 0.f;
-                    }
-                    if (nchw_vec) {
-                        const int64_t idx = ((int64_t)loc[uu].b0 * a.c_total + a.c_offset + c) * a.items_per_tile + loc[uu].r0;
-                        if (a.out_dtype == P3P_DTYPE_F32) {
-                            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(a.out) + idx);
-                            dst[0] = make_float4(ob[0], ob[1], ob[2], ob[3]);
-                            dst[1] = make_float4(ob[4], ob[5], ob[6], ob[7]);
+                mbar_arrive(&t_empty[ts]);
+                const float mB = fmaxf(max32(va), max32(vb));
+                if (quad == 0) PTL(9 + g, jn, 2);
+                const float bb = (m == 0) ? b1v[0] : ((m == 1) ? b1v[1] : b1v[2]);
+                const int c = m * 128 + cl;
+                // which of the pair's items hold a pillar: written by the front end before the pair's operands were released
+                const unsigned vv = *reinterpret_cast<const unsigned short*>(sValid + (p & (kValidRing - 1)) * 2);
+                const bool v0 = (vv & 0xFFu) != 0, v1 = (vv >> 8) != 0;
+                if (fast) {
+                    const float o0 = v0 ? fmaxf(mA + (g0 + bb), 0.f) : 0.f;
+                    const float o1 = v1 ? fmaxf(mB + (g1 + bb), 0.f) : 0.f;
+                    if (c < C) {
+                        if (nchw) {
+                            const int64_t i0 = ((int64_t)ub * a.c_total + a.c_offset + c) * ipt + ur + 2 * pr;
+                            if (f32) *reinterpret_cast<float2*>(static_cast<float*>(a.out) + i0) = make_float2(o0, o1);
+                            else *reinterpret_cast<uint32_t*>(static_cast<unsigned short*>(a.out) + i0) = pack_bf16(o0, o1);
+                        } else if (f32) {
+                            // (B, ny nx, C) rows: a warp writes 32 consecutive channels of each of the pair's two cells
+                            float* dst = static_cast<float*>(a.out) + (int64_t)item * C + c;
+                            dst[0] = o0;
+                            dst[C] = o1;
                         } else {
-                            uint4* dst = reinterpret_cast<uint4*>(static_cast<unsigned short*>(a.out) + idx);
-                            dst[0] = make_uint4(pack_bf16(ob[0], ob[1]), pack_bf16(ob[2], ob[3]), pack_bf16(ob[4], ob[5]), pack_bf16(ob[6], ob[7]));
+                            unsigned short* dst = static_cast<unsigned short*>(a.out) + (int64_t)item * C + c;
+                            dst[0] = (unsigned short)(pack_bf16(o0, 0.f) & 0xFFFF);
+                            dst[C] = (unsigned short)(pack_bf16(o1, 0.f) & 0xFFFF);
                         }
-                    } else if (canvas && rows_f32 && item0[uu] + kUnit <= total_items) {
-                        // (B, ny nx, C) rows: a warp writes 32 consecutive channels of one cell, 8 cells C floats apart
-                        float* dst = static_cast<float*>(a.out) + (int64_t)item0[uu] * C + c;
-#pragma unroll
-                        for (int i = 0; i < kUnit; ++i) dst[(int64_t)i * C] = ob[i];
-                    } else {
-                        int b = loc[uu].b0, r = loc[uu].r0;
-#pragma unroll
-                        for (int i = 0; i < kUnit; ++i) {
-                            const int item = item0[uu] + i;
-                            const bool v = (vmask[uu] >> i) & 1u;
-                            // list rows past num_pillars stay untouched; canvas cells are always written
-                            if (item < total_items && (v || canvas)) {
-                                const int64_t idx = nchw ? ((int64_t)b * a.c_total + a.c_offset + c) * a.items_per_tile + r
-                                                         : (int64_t)item * C + c;
-                                store_scalar(a, idx, ob[i]);
-                            }
-                            if (++r == a.items_per_tile) { r = 0; ++b; }
+                    }
+                } else {
+                    int b0 = ub, r0 = ur + 2 * pr, b1, r1;
+                    if (r0 >= ipt) { r0 -= ipt; ++b0; }
+                    b1 = b0; r1 = r0 + 1;
+                    if (r1 >= ipt) { r1 -= ipt; ++b1; }
+                    const float o0 = v0 ? fmaxf(mA + (g0 + bb), 0.f) : 0.f;
+                    const float o1 = v1 ? fmaxf(mB + (g1 + bb), 0.f) : 0.f;
+                    if (c < C) {
+                        if (nchw) {
+                            if (item < total_items) store_scalar(a, ((int64_t)b0 * a.c_total + a.c_offset + c) * ipt + r0, o0);
+                            if (item + 1 < total_items) store_scalar(a, ((int64_t)b1 * a.c_total + a.c_offset + c) * ipt + r1, o1);
+                        } else {
+                            // list rows past num_pillars stay untouched, canvas cells are always written
+                            const int64_t i0 = (int64_t)item * C + c;
+                            if (item < total_items && (v0 || canvas)) store_scalar(a, i0, o0);
+                            if (item + 1 < total_items && (v1 || canvas)) store_scalar(a, i0 + C, o1);
                         }
                     }
                 }
+                if (quad == 0) PTL(9 + g, jn, 3);
+                ++jn;
             }
         }
     }

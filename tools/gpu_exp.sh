@@ -1,8 +1,15 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-P3P_EXTRA_NVCC_FLAGS="-DP3P_TIMELINE -DP3P_EXP_NOFENCE" python -m pixelspointspolygons_b200.build --force > gpurun_out/build_tl.log 2>&1 || tail gpurun_out/build_tl.log
-timeout 300 python tools/pfn_timeline.py fp16 > gpurun_out/pfn_tl_fp16_nofence.txt 2>&1; echo "exit $?"
-tail -n 14 gpurun_out/pfn_tl_fp16_nofence.txt
-python -m pixelspointspolygons_b200.build --force > gpurun_out/build.log 2>&1
-bash tools/gpu_prof.sh pfn_tc prof_pfn
+for exp in "-DP3P_NOSPLIT" ""; do
+P3P_EXTRA_NVCC_FLAGS="$exp" python -m pixelspointspolygons_b200.build --force > gpurun_out/build_exp.log 2>&1 || tail gpurun_out/build_exp.log
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -p no:cacheprovider -k "pfn or encode or fusion" 2>&1 | tail -2
+for prec in fp16 tf32; do
+timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --precision $prec > gpurun_out/bench_exp.json 2> gpurun_out/bench_exp.err
+python - "$exp $prec" <<'PY'
+import json,sys
+d=json.loads(open("gpurun_out/bench_exp.json").read().strip().splitlines()[-1])
+print("EXP[%s]"%sys.argv[1], "ms/step", round(d["ms_per_step"],4), "stage_ms", d["stage_ms"])
+PY
+done
+done

@@ -36,15 +36,15 @@ for cta in range(2):
     t0 = a[a > 0].min()
     a = np.where(a > 0, a - t0, -1)
     print(f"==== CTA {cta} ({prec}); cycles relative to the first stamp")
-    print("MMA: pair: h_full_ok, t_empty0_ok, t_empty1_ok, t_empty2_ok")
+    print("MMA: pair: h_full_ok, t_empty_ok (first tile), issued")
     for p in list(range(0, 10)) + list(range(30, 44)):
-        print(f"  p={p:3d} ", a[0, p].tolist())
-    print("front end warp 0 / 1 (stage 0): j: loop_top, h_empty_ok, computed")
+        print(f"  p={p:3d} ", a[0, p, :3].tolist())
+    print("front end warp 0 / 1: j: loop_top, h_empty_ok, computed")
     for j in list(range(0, 4)) + list(range(8, 12)):
         print(f"  j={j:3d} ", a[1, j, :3].tolist(), a[2, j, :3].tolist())
-    print("epilogue group 0 / 1 / 2 lead warp: gp: wait_begin, t_full_ok, loads_done")
-    for gp in list(range(0, 10)) + list(range(30, 44)):
-        print(f"  gp={gp:3d} ", a[9, gp, :3].tolist(), a[10, gp, :3].tolist(), a[11, gp, :3].tolist())
+    print("epilogue group 0 / 1 lead warp: job: wait_begin, t_full_ok, loads_done, stored")
+    for gp in list(range(0, 8)) + list(range(36, 44)):
+        print(f"  job={gp:3d} ", a[9, gp, :4].tolist(), a[10, gp, :4].tolist(), a[11, gp, :4].tolist())
     mm = a[0, :, 0]
     ok = mm > 0
     d = np.diff(mm[ok])
@@ -53,9 +53,11 @@ for cta in range(2):
         c = a[r, :, 2] - a[r, :, 1]
         w = a[r, :, 1] - a[r, :, 0]
         okr = a[r, :, 2] > 0
-        print(f"front warp {r-1}: compute median {np.median(c[okr]):.0f}  wait h_empty median {np.median(w[okr]):.0f}  iters {okr.sum()}")
+        gap = a[r, 1:, 0] - a[r, :-1, 2]
+        print(f"front warp {r-1}: compute median {np.median(c[okr]):.0f}  wait h_empty median {np.median(w[okr]):.0f}  computed->next top median {np.median(gap[okr[1:]]):.0f}  iters {okr.sum()}")
     for r in range(9, 12):
         okr = a[r, :, 2] > 0
         w = a[r, :, 1] - a[r, :, 0]
         ld = a[r, :, 2] - a[r, :, 1]
-        print(f"epi group {r-9}: wait t_full median {np.median(w[okr]):.0f}  loads median {np.median(ld[okr]):.0f}  iters {okr.sum()}")
+        stt = a[r, :, 3] - a[r, :, 2]
+        print(f"epi group {r-9}: wait t_full median {np.median(w[okr]):.0f}  loads median {np.median(ld[okr]):.0f}  store median {np.median(stt[okr]):.0f}  jobs {okr.sum()}  last {a[r, :, 3].max()}")
