@@ -12,8 +12,8 @@
 //   * every lane hashes its <= 16 points (all loads in flight at once) with the reference's fp32 operation order;
 //     only the packed (key, rank) word of a point stays in a register.
 //   * each warp owns a contiguous segment of the chunk and counts it per key in a private shared-memory histogram,
-//     32 consecutive points per step: read count, write (count + 1 | lane tag), read back; the lane whose tag
-//     survived owns that count, the (rare) same-key losers of the step retry.  No atomics, no match.any.
+//     32 consecutive points per step: read the key's count, then one shared-memory atomic per point; same-key lanes
+//     of a step receive consecutive counts in arbitrary order.  No retry loops, no match.any.
 //   * the chunk's per-key counts are published to global memory and a flag is released; the CTA acquires the flags
 //     of the earlier chunks of its tile, sums their counts per key (exclusive prefix over chunks, then over its own
 //     warps) and walks its registers again: rank = base + rank-in-segment; survivors (rank < M) re-read their xyz
@@ -74,12 +74,6 @@ __device__ __forceinline__ unsigned lds_u16(uint32_t addr, int pred) {
         : "memory");
     return v;
 }
-__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned val, int pred) {
-    asm volatile(
-        "{\n .reg .pred p;\n .reg .b16 t;\n setp.ne.b32 p, %2, 0;\n cvt.u16.u32 t, %1;\n @p st.shared.u16 [%0], t;\n}" ::"r"(addr),
-        "r"(val), "r"(pred)
-        : "memory");
-}
 __device__ __forceinline__ unsigned lds_u32(uint32_t addr, int pred) {
     unsigned v;
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n mov.b32 %0, 0;\n @p ld.shared.u32 %0, [%1];\n}"
@@ -87,6 +81,19 @@ __device__ __forceinline__ unsigned lds_u32(uint32_t addr, int pred) {
                  : "r"(addr), "r"(pred)
                  : "memory");
     return v;
+}
+
+// predicated atomic increment of a 16-bit shared-memory counter (through its 32-bit word; counters never overflow into
+// their neighbour); returns the counter's previous value
+__device__ __forceinline__ unsigned atoms_add_u16(uint32_t addr, int pred) {
+    unsigned r;
+    const unsigned sh = (addr & 2u) * 8u;
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %3, 0;\n mov.b32 %0, 0;\n @p atom.shared.add.u32 %0, [%1], %2;\n}"
+        : "=r"(r)
+        : "r"(addr & ~3u), "r"(1u << sh), "r"(pred)
+        : "memory");
+    return (r >> sh) & 0xFFFFu;
 }
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
@@ -258,11 +265,13 @@ __device__ void plan_tile(const GridDev& g, const WsPtrs& ws, int b, int Keff, i
     }
 }
 
-// packed per-point word: key (13 bits) | rank inside the warp segment (10 bits) << 13 | retry round (5 bits) << 23
+// packed per-point word: key (13 bits) | count of the key before the point in the warp segment (10 bits) << 13 |
+// position among the same-key lanes of the point's step (5 bits) << 23
 constexpr int kKeyBits = 13, kOldBits = 10;
 constexpr unsigned kCntMask = (1u << kOldBits) - 1u;
 static_assert(kMaxKeys <= (1 << kKeyBits), "key field too narrow");
 static_assert(kMaxChunkPoints / kWarps <= (1 << (kOldBits - 1)), "segment count field too narrow");
+static_assert(kMaxChunkPoints * 8 < 65536, "8 chunk rows must add up inside 16-bit lanes");
 
 __global__ void __launch_bounds__(kThreads, 3)
 voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __restrict__ offsets, int B, GridDev g, int S,
@@ -270,7 +279,7 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = g.num_keys;
     const int Kp = ws.key_stride;  // K rounded up to 8: row stride of chunk_hist (16-byte rows)
-    // [kWarps][K]: walk 1: count (10 bits) | lane tag << 10; afterwards: points of the key in the earlier warps of the CTA
+    // [kWarps][K]: walk 1: points of the key in the warp's segment; afterwards: points of the key in the earlier warps of the CTA
     uint16_t* hist = reinterpret_cast<uint16_t*>(smem_raw);
     uint16_t* ctot_s = reinterpret_cast<uint16_t*>(smem_raw + (((size_t)kWarps * K * sizeof(uint16_t) + 15) / 16) * 16);  // [Kp] chunk totals
     unsigned* prefix_s = reinterpret_cast<unsigned*>(ctot_s + Kp);  // [Kp] points of the key in the earlier chunks of the tile
@@ -305,14 +314,12 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
     const float* seg_pts = pts + seg0 * stride;
 
     // ---- hash + walk 1, software pipelined: the loads of the second half are in flight while the first half is
-    //      counted.  Walk 1 = per-warp histogram of this warp's contiguous segment, 32 consecutive points per step:
-    //      read count, write (count + 1 | lane tag), read back; same-key lanes of a step get one owner per round.
+    //      counted.  Walk 1 = per-warp histogram of this warp's contiguous segment, 32 consecutive points per step.
     int pk[kIters];
     // bit 0: some key may lie outside the regular cells or be aliased (a point on a max face: z == z_max, y == y_max, ...)
     // bit 1: some point sits on the x / y max face (its run's coordinates are not decodable from the key)
     int hi_key = 0;
     constexpr int kBatch = kIters / 2;
-    const unsigned tag = (unsigned)lane << kOldBits;
     float px[kBatch], py[kBatch], pz[kBatch];
     auto load_batch = [&](int j0) {
 #pragma unroll
@@ -347,21 +354,13 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
             const int j = j0 + jj;
             if (j * 32 < seg_n) {  // warp-uniform
                 const int k = pk[j];
-                int pend = k >= 0 ? 1 : 0;
-                const uint32_t sa = myhist_sa + 2u * (unsigned)(pend ? k : 0);
-                unsigned myv = 0, myr = 0;
-                for (unsigned round = 0;; ++round) {
-                    const unsigned v = lds_u16(sa, pend) & kCntMask;
-                    const unsigned nv = (v + 1u) | tag;
-                    sts_u16(sa, nv, pend);
-                    __syncwarp();
-                    const int won = pend & (lds_u16(sa, pend) == nv ? 1 : 0);
-                    myv = won ? v : myv;
-                    myr = won ? round : myr;
-                    pend ^= won;
-                    if (!__any_sync(0xffffffffu, pend)) break;
-                }
-                if (k >= 0) pk[j] = k | (int)(myv << kKeyBits) | (int)(myr << (kKeyBits + kOldBits));
+                const int act = k >= 0 ? 1 : 0;
+                const uint32_t sa = myhist_sa + 2u * (unsigned)(act ? k : 0);
+                // count of the key before this step, then one atomic per point: same-key lanes of the step receive
+                // consecutive counts in arbitrary order (shared-memory operations of a warp execute in program order)
+                const unsigned before = lds_u16(sa, act);
+                const unsigned old = atoms_add_u16(sa, act);
+                if (act) pk[j] = k | (int)(old << kKeyBits) | (int)((old - before) << (kKeyBits + kOldBits));
             }
         }
     };
@@ -408,7 +407,7 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
         hi_key |= (__syncthreads_or(hi_before & 1) ? 1 : 0) | (__syncthreads_or(hi_before & 2) ? 2 : 0);
     }
     TL(blockIdx.x, 5);
-    // ---- prefix over the earlier chunks: 8 keys per thread with 16-byte L2 loads, 4 rows in flight per batch -----------
+    // ---- prefix over the earlier chunks: 8 keys per thread with 16-byte L2 loads, 8 rows in flight per batch -----------
     const int M = g.M;
     const bool last_chunk = (loc.c == loc.nchunks - 1);
     const int Kuse = (hi_key & 1) ? Kp : Kreg;  // keys that can be non-empty in this tile so far
@@ -418,15 +417,16 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
         if (k8 * 8 < Kuse) {
             const uint4* src = reinterpret_cast<const uint4*>(ws.chunk_hist + (size_t)loc.gstart * Kp) + k8;
             const size_t row = (size_t)Kp / 8;
-            for (int c0 = 0; c0 < loc.c; c0 += 4) {
-                uint4 v[4];
+            for (int c0 = 0; c0 < loc.c; c0 += 8) {
+                uint4 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = (c0 + u < loc.c) ? __ldcg(src + (size_t)(c0 + u) * row) : make_uint4(0, 0, 0, 0);
+                for (int u = 0; u < 8; ++u) v[u] = (c0 + u < loc.c) ? __ldcg(src + (size_t)(c0 + u) * row) : make_uint4(0, 0, 0, 0);
+                // 8 rows of 16-bit counts (<= 4096 each) add up inside their 16-bit lanes without a carry
+                uint4 sum = v[0];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    acc[0] += v[u].x & 0xFFFFu; acc[1] += v[u].x >> 16; acc[2] += v[u].y & 0xFFFFu; acc[3] += v[u].y >> 16;
-                    acc[4] += v[u].z & 0xFFFFu; acc[5] += v[u].z >> 16; acc[6] += v[u].w & 0xFFFFu; acc[7] += v[u].w >> 16;
-                }
+                for (int u = 1; u < 8; ++u) { sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w; }
+                acc[0] += sum.x & 0xFFFFu; acc[1] += sum.x >> 16; acc[2] += sum.y & 0xFFFFu; acc[3] += sum.y >> 16;
+                acc[4] += sum.z & 0xFFFFu; acc[5] += sum.z >> 16; acc[6] += sum.w & 0xFFFFu; acc[7] += sum.w >> 16;
             }
         }
 #pragma unroll
@@ -484,8 +484,12 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
     }
     // ---- walk 2: rank = earlier chunks + earlier warps + rank in segment; scatter the survivors ---------------------
     if (open_keys) {
-        // pass A: ranks (registers + shared memory only); pk[j] becomes key | rank << 13 for survivors, -1 otherwise
+        // pass A: ranks (registers + shared memory only); pk[j] becomes key | rank << 13 for survivors, -1 otherwise.
+        // Same-key lanes of a step own their ranks in arbitrary order, which only matters in the one step where the key
+        // crosses M: those steps are found with ONE warp vote for the whole chunk and re-ranked in lane (= index) order.
         const uint32_t prefix_sa = smem_u32(prefix_s);
+        constexpr int kRankBits = 11;  // provisional rank field (clamped): M + 31 < 2^11
+        unsigned cross = 0;
 #pragma unroll
         for (int j = 0; j < kIters; ++j) {
             if (j * 32 < seg_n) {  // warp-uniform
@@ -495,17 +499,25 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
                 const unsigned pre = act ? lds_u32(prefix_sa + 4u * (unsigned)kj, act) : (unsigned)M;
                 const unsigned wbase = lds_u16(myhist_sa + 2u * (unsigned)(act ? kj : 0), act);
                 unsigned rank = pre < (unsigned)M ? pre + wbase + (unsigned)old : (unsigned)M;
-                // same-key lanes of a step own their ranks in arbitrary order: re-rank in lane (= index) order in the
-                // one step where the key crosses M
-                const bool crossing = (rank >= (unsigned)M) && (rank < (unsigned)(M + rnd));
-                if (__any_sync(0xffffffffu, crossing)) {
-                    const unsigned m = __match_any_sync(0xffffffffu, kj);
-                    if (pre < (unsigned)M) rank = pre + wbase + (unsigned)(old - rnd) + (unsigned)__popc(m & ((1u << lane) - 1u));
-                }
-                pk[j] = (rank < (unsigned)M) ? (kj | (int)(rank << kKeyBits)) : -1;
+                if ((rank >= (unsigned)M) && (rank < (unsigned)(M + rnd))) cross |= 1u << j;
+                rank = rank < (1u << kRankBits) - 1u ? rank : (1u << kRankBits) - 1u;
+                pk[j] = act ? (kj | (int)(rank << kKeyBits) | (rnd << (kKeyBits + kRankBits))) : -1;
             } else {
                 pk[j] = -1;
             }
+        }
+        cross = __reduce_or_sync(0xffffffffu, cross);
+#pragma unroll
+        for (int j = 0; j < kIters; ++j) {
+            const int kj = pk[j] < 0 ? -1 : (pk[j] & ((1 << kKeyBits) - 1));
+            unsigned rank = (unsigned)(pk[j] >> kKeyBits) & ((1u << kRankBits) - 1u);
+            if (cross & (1u << j)) {  // warp-uniform, about 1 % of the steps
+                const unsigned rnd = (unsigned)(pk[j] >> (kKeyBits + kRankBits)) & 31u;
+                const unsigned m = __match_any_sync(0xffffffffu, kj);
+                // lanes of a run whose first count lies below M (the others keep a rank >= M)
+                if (kj >= 0 && rank - rnd < (unsigned)M) rank = rank - rnd + (unsigned)__popc(m & ((1u << lane) - 1u));
+            }
+            pk[j] = (kj >= 0 && rank < (unsigned)M) ? (kj | (int)(rank << kKeyBits)) : -1;
         }
         TL(blockIdx.x, 7);
         // pass B: survivors re-read their xyz (L1 / L2 hits), all loads of a batch in flight before the first store
