@@ -378,7 +378,10 @@ __device__ __forceinline__ float max32(const float (&v)[32]) {
 //                        into accumulator stage m (one elected thread issues)
 //   3 x 4 epilogue warps: group g reads accumulator stage g: tcgen05.ld, max over each
 //                        pillar's 64 columns with 3-input max, + W1b' hmax + b1, relu, store of the two cells.
-template <int kPrec>
+// kMode: 0 = any item source / layout / dtype (run-time branches); 1 = canvas items, whole units inside one tile, fp32 rows
+// of C channels (B, ny nx, C); 2 = the same into the fp32 NCHW (concat) buffer.  Modes 1 and 2 are the shipped encoder
+// configurations with every run-time branch of the steady-state loops resolved at compile time.
+template <int kPrec, int kMode>
 __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     using Cfg = TcCfg<kPrec>;
     constexpr bool kTf32 = Cfg::kTf32;
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     const int num_units = (total_items + kUnit - 1) / kUnit;
     const int my_units = (num_units > (int)blockIdx.x) ? (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int my_pairs = my_units * kPairsPerUnit;  // pairs this CTA processes, in order p = 0, 1, ...
-    const bool canvas = (a.item_mode == kItemsCanvas);
+    const bool canvas = (kMode != 0) || (a.item_mode == kItemsCanvas);
 
     // ---- one-time setup --------------------------------------------------------------------------
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -696,11 +699,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         // =========================== epilogue: group g owns channel tile g ===========================
         const int g = (warp - kEpiWarp0) >> 2;
         const int quad = warp & 3;  // TMEM lanes this warp may read: 32 * (warp id % 4)
-        const bool nchw = canvas && (a.out_layout == P3P_LAYOUT_NCHW);
-        const bool f32 = (a.out_dtype == P3P_DTYPE_F32);
+        const bool nchw = (kMode == 2) || (kMode == 0 && canvas && (a.out_layout == P3P_LAYOUT_NCHW));
+        const bool f32 = (kMode != 0) || (a.out_dtype == P3P_DTYPE_F32);
         const int C = a.bl.C, ipt = a.items_per_tile;
         // fast path: whole units inside one tile, every item exists -> no per-item bounds, two-cell vector stores
-        const bool fast = canvas && (total_items % kUnit == 0) && (ipt % kUnit == 0);  // (the front end marks items beyond the end invalid)
+        const bool fast = (kMode != 0) || (canvas && (total_items % kUnit == 0) && (ipt % kUnit == 0));
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int cl = quad * 32 + lane;  // channel inside a 128-channel tile
         float b1v[3];
@@ -825,23 +828,34 @@ int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st) {
     if (a.num_items > 0x7fffffff - 64) return fail(P3P_ERR_UNSUPPORTED, "%lld work items exceed the 32-bit item index", (long long)a.num_items);
     static bool attr_done = false;
     if (!attr_done) {
-        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<P3P_PRECISION_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)TcCfg<P3P_PRECISION_TF32>::kSmemBytes));
-        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<P3P_PRECISION_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)TcCfg<P3P_PRECISION_BF16>::kSmemBytes));
-        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<P3P_PRECISION_FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)TcCfg<P3P_PRECISION_FP16>::kSmemBytes));
+#define P3P_TC_ATTR(PREC, MODE)                                                                                         \
+    P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<PREC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)TcCfg<PREC>::kSmemBytes))
+        P3P_TC_ATTR(P3P_PRECISION_TF32, 0); P3P_TC_ATTR(P3P_PRECISION_TF32, 1); P3P_TC_ATTR(P3P_PRECISION_TF32, 2);
+        P3P_TC_ATTR(P3P_PRECISION_BF16, 0); P3P_TC_ATTR(P3P_PRECISION_BF16, 1); P3P_TC_ATTR(P3P_PRECISION_BF16, 2);
+        P3P_TC_ATTR(P3P_PRECISION_FP16, 0); P3P_TC_ATTR(P3P_PRECISION_FP16, 1); P3P_TC_ATTR(P3P_PRECISION_FP16, 2);
+#undef P3P_TC_ATTR
         attr_done = true;
     }
     const int64_t units = (a.num_items + kUnit - 1) / kUnit;
     int64_t grid = device_sm_count();
     if (grid > units) grid = units;
-    if (precision == P3P_PRECISION_TF32)
-        pfn_tc_kernel<P3P_PRECISION_TF32><<<(unsigned)grid, kTcThreads, TcCfg<P3P_PRECISION_TF32>::kSmemBytes, st>>>(a);
-    else if (precision == P3P_PRECISION_BF16)
-        pfn_tc_kernel<P3P_PRECISION_BF16><<<(unsigned)grid, kTcThreads, TcCfg<P3P_PRECISION_BF16>::kSmemBytes, st>>>(a);
-    else
-        pfn_tc_kernel<P3P_PRECISION_FP16><<<(unsigned)grid, kTcThreads, TcCfg<P3P_PRECISION_FP16>::kSmemBytes, st>>>(a);
+    int mode = 0;
+    if (a.item_mode == kItemsCanvas && a.num_items % kUnit == 0 && a.items_per_tile % kUnit == 0 && a.out_dtype == P3P_DTYPE_F32)
+        mode = (a.out_layout == P3P_LAYOUT_NCHW) ? 2 : 1;
+#define P3P_LAUNCH_TC(PREC, MODE) \
+    pfn_tc_kernel<PREC, MODE><<<(unsigned)grid, kTcThreads, TcCfg<PREC>::kSmemBytes, st>>>(a)
+#define P3P_LAUNCH_TC_MODES(PREC)                         \
+    do {                                                  \
+        if (mode == 1) P3P_LAUNCH_TC(PREC, 1);            \
+        else if (mode == 2) P3P_LAUNCH_TC(PREC, 2);       \
+        else P3P_LAUNCH_TC(PREC, 0);                      \
+    } while (0)
+    if (precision == P3P_PRECISION_TF32) P3P_LAUNCH_TC_MODES(P3P_PRECISION_TF32);
+    else if (precision == P3P_PRECISION_BF16) P3P_LAUNCH_TC_MODES(P3P_PRECISION_BF16);
+    else P3P_LAUNCH_TC_MODES(P3P_PRECISION_FP16);
+#undef P3P_LAUNCH_TC_MODES
+#undef P3P_LAUNCH_TC
     P3P_CUDA_CHECK(cudaGetLastError());
     return P3P_OK;
 }
