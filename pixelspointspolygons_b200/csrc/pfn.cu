@@ -288,10 +288,17 @@ __global__ void zero_lidar_kernel(PfnArgs a) {
 // tensor-core kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kNF = 8;                         // front-end warps: warp w takes item w of every unit
-constexpr int kMmaWarps = 3;                   // warp m < 3: MMA issue for channel tile m (warp 0 also owns the TMEM allocation)
+constexpr int kMmaWarps = 4;                   // warp group 0: warp m < 3 issues the MMAs of channel tile m (warp 0 also owns the TMEM allocation), warp 3 idles
 constexpr int kEpiWarp0 = kMmaWarps + kNF;     // then kNF front-end warps, then the epilogue warps
 constexpr int kEpiGroups = 3;                  // epilogue groups of 4 warps (one warp per TMEM lane quarter)
 constexpr int kTcThreads = 32 * (kEpiWarp0 + 4 * kEpiGroups);
+#ifndef P3P_REG_MMA
+#define P3P_REG_MMA 40
+#define P3P_REG_FRONT 120
+#define P3P_REG_EPI 64
+#endif
+constexpr int kRegMma = P3P_REG_MMA, kRegFront = P3P_REG_FRONT, kRegEpi = P3P_REG_EPI;  // registers per thread after setmaxnreg (launch: 80)
+static_assert(4 * kRegMma + 8 * kRegFront + 12 * kRegEpi <= 24 * 80, "register pool of the launch exceeded");
 constexpr int kUnit = 8;                       // items per unit = 4 pillar pairs, consecutive canvas cells
 constexpr int kPairsPerUnit = kUnit / 2;
 constexpr int kTmemStage = 144;                // TMEM columns per accumulator stage: 128 (pillar pair) + 16 (W1b' hmax of the pair)
@@ -342,6 +349,10 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -443,7 +454,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register budget per role (warp groups of 4 warps): the launch allots 80 registers per thread; the issuers and the
+    // epilogue hand registers back, the front end (long independent FMA chains) takes them.  Measured splits
+    // (MMA / front / epilogue -> fp16, tf32 kernel time): 40/112/72 -> 43.3, 68.9 us; 40/120/64 -> 43.9, 52.4 us;
+    // 40/136/56 -> 44.6, 53.1 us; 24/104/80 -> 78.6, 55.2 us (the issuers spill below 32); no reallocation -> 47.1, 56.4 us.
     if (warp < kMmaWarps) {
+        setmaxnreg_dec<kRegMma>();
         // =========================== MMA issuers: warp m owns channel tile m and accumulator stage m ===========================
         // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers); one elected
         // lane issues the tcgen05 instructions and their commits.  One issuing warp per tile keeps the per-pair chain of
@@ -495,6 +511,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         // lane's 8 channels (one 16-byte chunk of a 16-bit operand row, two chunks of a tf32 row).  The pillar's points
         // arrive by cp.async (zero-filled beyond n) into a per-warp double buffer one item ahead; the descriptor word is
         // loaded two items ahead and decoded one iteration later; the channel constants of layer 0 sit in registers.
+        setmaxnreg_inc<kRegFront>();
         const int fw = warp - kMmaWarps, half = fw & 1, pr = fw >> 1;
         const int o = lane & 3, pt = lane >> 2;
         float2 ux[4], uy[4], uz[4];
@@ -697,6 +714,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         }
     } else {
         // =========================== epilogue: group g owns channel tile g ===========================
+        if constexpr (kRegEpi < 80) setmaxnreg_dec<kRegEpi>();
         const int g = (warp - kEpiWarp0) >> 2;
         const int quad = warp & 3;  // TMEM lanes this warp may read: 32 * (warp id % 4)
         const bool nchw = (kMode == 2) || (kMode == 0 && canvas && (a.out_layout == P3P_LAYOUT_NCHW));
