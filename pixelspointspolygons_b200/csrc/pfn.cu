@@ -453,6 +453,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above reads only the prepared weights; the voxelizer's tables and slots are read from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // Register budget per role (warp groups of 4 warps): the launch allots 80 registers per thread; the issuers and the
     // epilogue hand registers back, the front end (long independent FMA chains) takes them.  Measured splits
@@ -861,8 +863,22 @@ int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st) {
     int mode = 0;
     if (a.item_mode == kItemsCanvas && a.num_items % kUnit == 0 && a.items_per_tile % kUnit == 0 && a.out_dtype == P3P_DTYPE_F32)
         mode = (a.out_layout == P3P_LAYOUT_NCHW) ? 2 : 1;
-#define P3P_LAUNCH_TC(PREC, MODE) \
-    pfn_tc_kernel<PREC, MODE><<<(unsigned)grid, kTcThreads, TcCfg<PREC>::kSmemBytes, st>>>(a)
+    // Programmatic dependent launch: the CTAs start (TMEM allocation, barriers, weights -> shared memory) while the
+    // voxelizer's last chunks drain, and wait for its results with griddepcontrol.wait before their first read.
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define P3P_LAUNCH_TC(PREC, MODE)                      \
+    do {                                               \
+        cfg.dynamicSmemBytes = TcCfg<PREC>::kSmemBytes; \
+        P3P_CUDA_CHECK(cudaLaunchKernelEx(&cfg, pfn_tc_kernel<PREC, MODE>, a)); \
+    } while (0)
 #define P3P_LAUNCH_TC_MODES(PREC)                         \
     do {                                                  \
         if (mode == 1) P3P_LAUNCH_TC(PREC, 1);            \

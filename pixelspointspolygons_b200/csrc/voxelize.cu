@@ -275,7 +275,7 @@ static_assert(kMaxChunkPoints * 8 < 65536, "8 chunk rows must add up inside 16-b
 
 __global__ void __launch_bounds__(kThreads, 3)
 voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __restrict__ offsets, int B, GridDev g, int S,
-                WsPtrs ws, int32_t* __restrict__ point_hash, int need_plan) {
+                WsPtrs ws, int32_t* __restrict__ point_hash, int need_plan, int pdl_from) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = g.num_keys;
     const int Kp = ws.key_stride;  // K rounded up to 8: row stride of chunk_hist (16-byte rows)
@@ -297,6 +297,11 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
     }
     __syncthreads();
     const int ticket = s_ticket;
+    // Let the dependent PFN grid start its prologue on the SMs this grid has left (it waits for this grid's completion
+    // with griddepcontrol.wait before it reads anything written here).  Only the last tickets trigger early: the
+    // dependent grid launches once every CTA has triggered or exited, i.e. when no CTA of this grid is still waiting
+    // for an SM that a waiting PFN CTA could occupy.
+    if (ticket >= pdl_from) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (w == 0) locate_chunk(ticket, offsets, B, S, &loc);
     // tiles without points have no chunk: ticket t < B writes the empty plan of tile t
     if (ticket < B && offsets[ticket + 1] <= offsets[ticket]) write_empty_tile(g, ws, ticket);
@@ -624,7 +629,8 @@ int launch_voxelize(const float* pts, int stride, const int64_t* offsets, int B,
     }
     // ticket counter, chunk flags and per-tile completion counters start at zero for every call
     P3P_CUDA_CHECK(cudaMemsetAsync(ws.sync, 0, l.sync_bytes, st));
-    voxelize_kernel<<<l.max_chunks, kThreads, smem, st>>>(pts, stride, offsets, B, g, l.chunk_points, ws, point_hash, need_plan);
+    const int pdl_from = l.max_chunks - device_sm_count();  // tickets of the last (partial) wave
+    voxelize_kernel<<<l.max_chunks, kThreads, smem, st>>>(pts, stride, offsets, B, g, l.chunk_points, ws, point_hash, need_plan, pdl_from);
     P3P_CUDA_CHECK(cudaGetLastError());
     return P3P_OK;
 }
