@@ -90,6 +90,7 @@ class EarlyFusionFrontEnd(nn.Module):
         self.image_embed = PatchEmbed(img_size=int(_get(enc, "in_size", enc.in_height)), patch_size=int(_get(enc, "patch_size", 8)),
                                       in_chans=3, embed_dim=dim, precision=self.lidar_embed.precision)
         self.channels = dim
+        self._side_streams = {}
 
     def _dropout_now(self) -> bool:
         """early_fusion_vit.py:113-119 (one draw per forward, whole batch)."""
@@ -102,8 +103,18 @@ class EarlyFusionFrontEnd(nn.Module):
         """Eval-mode fused path: both halves written in place into `out` (B, 2C, ny, nx); returns `out`."""
         dim = self.channels
         lidar_zero = self._dropout_now() if lidar_zero is None else bool(lidar_zero)
-        self.image_embed.forward_into(x_image, out, 2 * dim, 0)
+        # the two halves are independent until the concat: the patch embedding runs on a side stream next to the
+        # voxelizer + PFN (fork / join by events, so a CUDA graph captures them as parallel branches)
+        dev = out.device
+        cur = torch.cuda.current_stream(dev)
+        side = self._side_streams.get(dev)
+        if side is None:
+            side = self._side_streams[dev] = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.image_embed.forward_into(x_image, out, 2 * dim, 0)
         self.lidar_embed.encode_into(x_lidar, out, P3P_LAYOUT_NCHW, c_total=2 * dim, c_offset=dim, lidar_zero=lidar_zero)
+        cur.wait_stream(side)
         return out
 
     def forward(self, x_image, x_lidar):
