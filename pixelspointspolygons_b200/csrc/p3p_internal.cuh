@@ -170,6 +170,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // cell hash of one point, or -1 (Open3D VoxelizeCPU HashFn; fp32 subtract then multiply, truncation)
 // `edge` is set when the point sits on the x or y max face (cell index == extent): only such points make a hash
 // ambiguous (cx == ext_x aliases (0, cy + 1); cy == ext_y aliases (cx, 0, cz + 1)).
+template <bool kCheckOverflow = true>
 __device__ __forceinline__ int point_key(const GridDev& g, float x, float y, float z, bool& edge) {
     const bool valid = (x >= g.mn[0]) && (x <= g.mx[0]) && (y >= g.mn[1]) && (y <= g.mx[1]) && (z >= g.mn[2]) &&
                        (z <= g.mx[2]);
@@ -179,7 +180,7 @@ __device__ __forceinline__ int point_key(const GridDev& g, float x, float y, flo
     const int cy = __float2int_rz(__fmul_rn(__fsub_rn(y, g.mn[1]), g.inv[1]));
     const int cz = __float2int_rz(__fmul_rn(__fsub_rn(z, g.mn[2]), g.inv[2]));
     const int h = cx + cy * g.stride1 + cz * g.stride2;
-    if ((g.flags & kFlagDropOverflow) && h >= g.num_cells) return -1;
+    if (kCheckOverflow && (g.flags & kFlagDropOverflow) && h >= g.num_cells) return -1;
     edge = (cx >= g.ext[0]) || (cy >= g.ext[1]);
     return h;
 }

@@ -273,26 +273,30 @@ static_assert(kMaxKeys <= (1 << kKeyBits), "key field too narrow");
 static_assert(kMaxChunkPoints / kWarps <= (1 << (kOldBits - 1)), "segment count field too narrow");
 static_assert(kMaxChunkPoints * 8 < 65536, "8 chunk rows must add up inside 16-bit lanes");
 
+// kFast: packed xyz (stride 3), no per-point hash export, hashes beyond the cells kept (the shipped configuration): the
+// per-point branches on those options are resolved at compile time.
+template <bool kFast>
 __global__ void __launch_bounds__(kThreads, 3)
-voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __restrict__ offsets, int B, GridDev g, int S,
+voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __restrict__ offsets, int B, GridDev g, int S,
                 WsPtrs ws, int32_t* __restrict__ point_hash, int need_plan, int pdl_from) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = g.num_keys;
     const int Kp = ws.key_stride;  // K rounded up to 8: row stride of chunk_hist (16-byte rows)
-    // [kWarps][K]: walk 1: points of the key in the warp's segment; afterwards: points of the key in the earlier warps of the CTA
+    // [kWarps][Kp] (16-byte rows): walk 1: points of the key in the warp's segment; afterwards: points of the key in the earlier warps of the CTA
     uint16_t* hist = reinterpret_cast<uint16_t*>(smem_raw);
-    uint16_t* ctot_s = reinterpret_cast<uint16_t*>(smem_raw + (((size_t)kWarps * K * sizeof(uint16_t) + 15) / 16) * 16);  // [Kp] chunk totals
+    uint16_t* ctot_s = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kWarps * Kp * sizeof(uint16_t));  // [Kp] chunk totals
     unsigned* prefix_s = reinterpret_cast<unsigned*>(ctot_s + Kp);  // [Kp] points of the key in the earlier chunks of the tile
     __shared__ ChunkLoc loc;
     __shared__ int s_ticket, s_last, s_runs[2];
     __shared__ int warp_tot[kWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int stride = kFast ? 3 : stride_arg;
     TL(blockIdx.x, 0);
     if (tid == 0) s_ticket = (int)atomicAdd(ws.sync, 1u);
     {
         uint4* h4 = reinterpret_cast<uint4*>(hist);
-        const int n16 = (kWarps * K * (int)sizeof(uint16_t) + 15) / 16;
+        const int n16 = kWarps * Kp * (int)sizeof(uint16_t) / 16;
         for (int i = tid; i < n16; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
@@ -314,7 +318,7 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
     const int segS = S / kWarps;  // multiple of 32
     const long long seg0 = loc.p0 + (long long)w * segS;
     const int seg_n = (int)(((seg0 + segS < loc.p1) ? seg0 + segS : loc.p1) - seg0);  // points of this warp (may be <= 0)
-    uint16_t* myhist = hist + (size_t)w * K;
+    uint16_t* myhist = hist + (size_t)w * Kp;
     uint8_t* edge = ws.edge + (size_t)loc.b * K;
     const float* seg_pts = pts + seg0 * stride;
 
@@ -344,11 +348,11 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
             pk[j] = -1;
             if (i < seg_n) {
                 bool on_edge;
-                const int k = point_key(g, px[jj], py[jj], pz[jj], on_edge);
+                const int k = point_key<!kFast>(g, px[jj], py[jj], pz[jj], on_edge);  // (kFast: the launcher checked the overflow flag)
                 pk[j] = k;
                 if (on_edge) edge[k] = 1;  // idempotent flag, read by the tile's plan
                 hi_key |= ((k >= g.num_cells) ? 1 : 0) | (on_edge ? 3 : 0);
-                if (point_hash) point_hash[seg0 + i] = k;
+                if (!kFast && point_hash) point_hash[seg0 + i] = k;
             }
         }
     };
@@ -382,20 +386,20 @@ voxelize_kernel(const float* __restrict__ pts, int stride, const int64_t* __rest
     // ---- publish this chunk's per-key counts (full rows: zeros beyond the keys in use) ------------------------------
     const int Kreg = (g.num_cells + 7) / 8 * 8 < Kp ? (g.num_cells + 7) / 8 * 8 : Kp;  // regular cells, 16-byte granular
     {
-        uint16_t* dst = ws.chunk_hist + (size_t)ticket * Kp;
-        const int Kmine = (hi_key & 1) ? Kp : Kreg;
-        for (int k = tid; k < Kp; k += kThreads) {
-            unsigned s = 0;
-            if (k < Kmine && k < K) {
+        // 8 keys per thread: 16-byte rows, counts added inside their 16-bit lanes (a chunk holds <= 4096 points);
+        // keys nobody hashed to stay zero, so the published rows are complete
+        uint4* dst = reinterpret_cast<uint4*>(ws.chunk_hist + (size_t)ticket * Kp);
+        for (int k8 = tid; k8 < Kp / 8; k8 += kThreads) {
+            uint4 acc = make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int ww = 0; ww < kWarps; ++ww) {
-                    const unsigned t = hist[(size_t)ww * K + k] & kCntMask;
-                    hist[(size_t)ww * K + k] = (uint16_t)s;  // points of the key in the earlier warps
-                    s += t;
-                }
+            for (int ww = 0; ww < kWarps; ++ww) {
+                uint4* cell = reinterpret_cast<uint4*>(hist + (size_t)ww * Kp) + k8;
+                const uint4 t = *cell;
+                *cell = acc;  // points of the keys in the earlier warps
+                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
             }
-            ctot_s[k] = (uint16_t)s;
-            dst[k] = (uint16_t)s;
+            reinterpret_cast<uint4*>(ctot_s)[k8] = acc;
+            dst[k8] = acc;
         }
         __threadfence();
         __syncthreads();
@@ -613,7 +617,7 @@ export_kernel(GridDev g, int B, WsPtrs ws, p3p_voxel_outputs out) {
 
 static size_t voxelize_smem_bytes(const GridDev& g) {
     const size_t kp = ((size_t)g.num_keys + 7) / 8 * 8;
-    const size_t hist = ((size_t)kWarps * g.num_keys * sizeof(uint16_t) + 15) / 16 * 16 + kp * (sizeof(uint16_t) + sizeof(unsigned));
+    const size_t hist = (size_t)kWarps * kp * sizeof(uint16_t) + kp * (sizeof(uint16_t) + sizeof(unsigned));
     const size_t plan = (size_t)(4 * g.num_keys + g.ny * g.nx) * sizeof(int);
     return ((hist > plan ? hist : plan) + 15) / 16 * 16;
 }
@@ -624,13 +628,17 @@ int launch_voxelize(const float* pts, int stride, const int64_t* offsets, int B,
     const size_t smem = voxelize_smem_bytes(g);
     static bool attr_done = false;
     if (!attr_done) {
-        P3P_CUDA_CHECK(cudaFuncSetAttribute(voxelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        P3P_CUDA_CHECK(cudaFuncSetAttribute(voxelize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        P3P_CUDA_CHECK(cudaFuncSetAttribute(voxelize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
     }
     // ticket counter, chunk flags and per-tile completion counters start at zero for every call
     P3P_CUDA_CHECK(cudaMemsetAsync(ws.sync, 0, l.sync_bytes, st));
     const int pdl_from = l.max_chunks - device_sm_count();  // tickets of the last (partial) wave
-    voxelize_kernel<<<l.max_chunks, kThreads, smem, st>>>(pts, stride, offsets, B, g, l.chunk_points, ws, point_hash, need_plan, pdl_from);
+    if (stride == 3 && point_hash == nullptr && !(g.flags & kFlagDropOverflow))
+        voxelize_kernel<true><<<l.max_chunks, kThreads, smem, st>>>(pts, stride, offsets, B, g, l.chunk_points, ws, point_hash, need_plan, pdl_from);
+    else
+        voxelize_kernel<false><<<l.max_chunks, kThreads, smem, st>>>(pts, stride, offsets, B, g, l.chunk_points, ws, point_hash, need_plan, pdl_from);
     P3P_CUDA_CHECK(cudaGetLastError());
     return P3P_OK;
 }
