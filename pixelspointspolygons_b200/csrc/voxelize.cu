@@ -342,6 +342,7 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
         }
     };
     auto hash_batch = [&](int j0) {
+        unsigned edge_bits = 0;  // points on the x / y max face (rare: one vote per batch, flags set on a slow path)
 #pragma unroll
         for (int jj = 0; jj < kBatch; ++jj) {
             const int j = j0 + jj, i = j * 32 + lane;
@@ -350,10 +351,15 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
                 bool on_edge;
                 const int k = point_key<!kFast>(g, px[jj], py[jj], pz[jj], on_edge);  // (kFast: the launcher checked the overflow flag)
                 pk[j] = k;
-                if (on_edge) edge[k] = 1;  // idempotent flag, read by the tile's plan
+                edge_bits |= on_edge ? (1u << j) : 0u;
                 hi_key |= ((k >= g.num_cells) ? 1 : 0) | (on_edge ? 3 : 0);
                 if (!kFast && point_hash) point_hash[seg0 + i] = k;
             }
+        }
+        if (__any_sync(0xffffffffu, edge_bits != 0)) {
+#pragma unroll
+            for (int jj = 0; jj < kBatch; ++jj)
+                if ((edge_bits >> (j0 + jj)) & 1u) edge[pk[j0 + jj]] = 1;  // idempotent flag, read by the tile's plan
         }
     };
     const uint32_t myhist_sa = smem_u32(myhist);
@@ -426,10 +432,11 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
         if (k8 * 8 < Kuse) {
             const uint4* src = reinterpret_cast<const uint4*>(ws.chunk_hist + (size_t)loc.gstart * Kp) + k8;
             const size_t row = (size_t)Kp / 8;
-            for (int c0 = 0; c0 < loc.c; c0 += 8) {
+            const uint4* rp = src;
+            for (int c0 = 0; c0 < loc.c; c0 += 8, rp += 8 * row) {
                 uint4 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (c0 + u < loc.c) ? __ldcg(src + (size_t)(c0 + u) * row) : make_uint4(0, 0, 0, 0);
+                for (int u = 0; u < 8; ++u) v[u] = (c0 + u < loc.c) ? __ldcg(rp + u * row) : make_uint4(0, 0, 0, 0);
                 // 8 rows of 16-bit counts (<= 4096 each) add up inside their 16-bit lanes without a carry
                 uint4 sum = v[0];
 #pragma unroll

@@ -170,6 +170,36 @@ def test_other_channel_widths(cuda_device, C):
     assert_close(a, r, 1e-3, f"C={C}")
 
 
+@pytest.mark.parametrize("prec", ["tf32", "fp16"])
+def test_odd_canvas_takes_the_general_path(cuda_device, prec):
+    """216 px tiles -> 27 x 27 = 729 cells: units of 8 cells straddle tiles and the last unit is partial, so the
+    tensor-core kernel runs its general mode (per-item bounds, scalar stores) in both layouts."""
+    grid = po.GridSpec(in_width=216.0, in_height=216.0, output_shape=(27, 27), max_voxels=(729, 729))
+    C = 384
+    cfg = default_cfg(device=str(cuda_device), in_size=216, max_num_voxels=grid.max_voxels, p3p_precision=prec)
+    enc = PointPillarsEncoder(cfg, voxel_encoder={"in_channels": 3, "feat_channels": [64, C]},
+                              scatter={"in_channels": C, "output_shape": [27, 27]}).to(cuda_device).eval()
+    sd, _ = po.synth_weights(21, feat_channels=(64, C))
+    enc.load_state_dict(sd)
+    ref = po.OraclePointPillarsEncoder(grid).eval()
+    ref.load_state_dict(sd)
+    tiles = []
+    for i, n in enumerate((9000, 40, 20000)):
+        t = po.synth_tile(n, 700 + i, clustered=(i == 2))
+        t[:, :2] *= np.float32(216.0 / 224.0)
+        tiles.append(t)
+    with torch.no_grad():
+        rv, rn, rc, _ = ref.voxelize(tiles)
+        gv, gn, gc = enc.voxelize(to_nested(tiles, cuda_device))
+        assert torch.equal(gc.cpu(), rc) and torch.equal(gn.cpu(), rn) and torch.equal(gv.cpu(), rv)
+        r_rows = ref(tiles)
+        r_nchw = ref(tiles, return_flattened=False)
+        a_rows = enc(to_nested(tiles, cuda_device))
+        a_nchw = enc(to_nested(tiles, cuda_device), return_flattened=False)
+    assert_close(a_rows, r_rows, TOL[prec], f"rows {prec}")
+    assert_close(a_nchw, r_nchw, TOL[prec], f"nchw {prec}")
+
+
 def test_full_size_batch_properties(cuda_device):
     """BASELINE config 2 (B=16, N=100k): properties that do not need the oracle at full size + oracle on 2 tiles."""
     grid = po.GridSpec()
