@@ -111,17 +111,23 @@ class ClockSampler:
         except Exception:
             self.nvml = None
 
-    def _poll(self):
+    def sample(self):
+        """One NVML reading; also called inline from the timed loop (the polling thread can starve behind the GIL)."""
         n = self.nvml
-        while not self.stop_flag:
+        if n is None:
+            return
+        try:
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
             try:
-                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
-                self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
             except Exception:
-                try:
-                    self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                except Exception:
-                    pass
+                pass
+
+    def _poll(self):
+        while not self.stop_flag:
+            self.sample()
             time.sleep(0.002)
 
     def start(self):
@@ -332,8 +338,11 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    every = max(1, args.steps // 16)
     for i in range(args.steps):
         run_step(i)
+        if i % every == every - 1:
+            sampler.sample()  # the launches run ahead of the device: the reading falls inside the timed region
     e1.record()
     barrier()
     clocks = sampler.stop()

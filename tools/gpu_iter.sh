@@ -22,3 +22,4 @@ for f in ("bench_fp16","bench_tf32","bench_fusion_fp16"):
     except Exception as e:
         print(f, "ERR", e); print(open(f"gpurun_out/{f}.err").read()[-2000:])
 PY
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -n 5 gpurun_out/smoke.log
