@@ -338,11 +338,13 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    every = max(1, args.steps // 16)
+    # up to three inline readings (an NVML call takes about a millisecond: only while the device has that much work
+    # queued behind it, so the timed region never waits for the host)
+    inline = {args.steps // 4, args.steps // 2, (3 * args.steps) // 4} if args.steps >= 64 else set()
     for i in range(args.steps):
         run_step(i)
-        if i % every == every - 1:
-            sampler.sample()  # the launches run ahead of the device: the reading falls inside the timed region
+        if i in inline:
+            sampler.sample()
     e1.record()
     barrier()
     clocks = sampler.stop()

@@ -172,17 +172,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // ambiguous (cx == ext_x aliases (0, cy + 1); cy == ext_y aliases (cx, 0, cz + 1)).
 template <bool kCheckOverflow = true>
 __device__ __forceinline__ int point_key(const GridDev& g, float x, float y, float z, bool& edge) {
-    const bool valid = (x >= g.mn[0]) && (x <= g.mx[0]) && (y >= g.mn[1]) && (y <= g.mx[1]) && (z >= g.mn[2]) &&
-                       (z <= g.mx[2]);
-    edge = false;
-    if (!valid) return -1;
+    // branch-free: the cell indices of an invalid point (NaN, out of range) are garbage and masked below
+    const bool valid = (x >= g.mn[0]) & (x <= g.mx[0]) & (y >= g.mn[1]) & (y <= g.mx[1]) & (z >= g.mn[2]) & (z <= g.mx[2]);
     const int cx = __float2int_rz(__fmul_rn(__fsub_rn(x, g.mn[0]), g.inv[0]));
     const int cy = __float2int_rz(__fmul_rn(__fsub_rn(y, g.mn[1]), g.inv[1]));
     const int cz = __float2int_rz(__fmul_rn(__fsub_rn(z, g.mn[2]), g.inv[2]));
     const int h = cx + cy * g.stride1 + cz * g.stride2;
-    if (kCheckOverflow && (g.flags & kFlagDropOverflow) && h >= g.num_cells) return -1;
-    edge = (cx >= g.ext[0]) || (cy >= g.ext[1]);
-    return h;
+    bool ok = valid;
+    if (kCheckOverflow) ok = ok & !((g.flags & kFlagDropOverflow) && h >= g.num_cells);
+    edge = ok & ((cx >= g.ext[0]) | (cy >= g.ext[1]));
+    return ok ? h : -1;
 }
 
 __device__ __forceinline__ void point_cell(const GridDev& g, float x, float y, float z, int& cx, int& cy, int& cz) {

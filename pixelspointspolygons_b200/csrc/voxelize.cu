@@ -27,6 +27,8 @@
 //     (last pillar in voxel order wins a cell, Appendix A.5).
 //
 // export_kernel (optional) dumps the reference-shaped tensors for the parity tests.
+#include <type_traits>
+
 #include "p3p_internal.cuh"
 
 namespace p3p {
@@ -330,24 +332,29 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
     int hi_key = 0;
     constexpr int kBatch = kIters / 2;
     float px[kBatch], py[kBatch], pz[kBatch];
-    auto load_batch = [&](int j0) {
+    // `full` (a std::bool_constant) resolves the bounds tests of a full 512-point segment at compile time: straight-line
+    // code, loads at immediate offsets from one lane pointer (every chunk but the last of a tile).
+    const float* lane_pts = seg_pts + (size_t)lane * stride;
+    auto load_batch = [&](int j0, auto full) {
+        constexpr bool kFull = decltype(full)::value;
 #pragma unroll
         for (int jj = 0; jj < kBatch; ++jj) {
             const int i = (j0 + jj) * 32 + lane;
-            px[jj] = 0.f; py[jj] = 0.f; pz[jj] = 0.f;
-            if (i < seg_n) {
-                const float* p = seg_pts + (size_t)i * stride;
+            if (!kFull) { px[jj] = 0.f; py[jj] = 0.f; pz[jj] = 0.f; }
+            if (kFull || i < seg_n) {
+                const float* p = lane_pts + (size_t)((j0 + jj) * 32) * stride;
                 px[jj] = __ldg(p); py[jj] = __ldg(p + 1); pz[jj] = __ldg(p + 2);
             }
         }
     };
-    auto hash_batch = [&](int j0) {
+    auto hash_batch = [&](int j0, auto full) {
+        constexpr bool kFull = decltype(full)::value;
         unsigned edge_bits = 0;  // points on the x / y max face (rare: one vote per batch, flags set on a slow path)
 #pragma unroll
         for (int jj = 0; jj < kBatch; ++jj) {
             const int j = j0 + jj, i = j * 32 + lane;
             pk[j] = -1;
-            if (i < seg_n) {
+            if (kFull || i < seg_n) {
                 bool on_edge;
                 const int k = point_key<!kFast>(g, px[jj], py[jj], pz[jj], on_edge);  // (kFast: the launcher checked the overflow flag)
                 pk[j] = k;
@@ -363,11 +370,12 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
         }
     };
     const uint32_t myhist_sa = smem_u32(myhist);
-    auto count_batch = [&](int j0) {
+    auto count_batch = [&](int j0, auto full) {
+        constexpr bool kFull = decltype(full)::value;
 #pragma unroll
         for (int jj = 0; jj < kBatch; ++jj) {
             const int j = j0 + jj;
-            if (j * 32 < seg_n) {  // warp-uniform
+            if (kFull || j * 32 < seg_n) {  // warp-uniform
                 const int k = pk[j];
                 const int act = k >= 0 ? 1 : 0;
                 const uint32_t sa = myhist_sa + 2u * (unsigned)(act ? k : 0);
@@ -379,13 +387,17 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
             }
         }
     };
-    load_batch(0);
-    hash_batch(0);
-    load_batch(kBatch);
-    TL(blockIdx.x, 2);
-    count_batch(0);
-    hash_batch(kBatch);
-    count_batch(kBatch);
+    auto walk1 = [&](auto full) {
+        load_batch(0, full);
+        hash_batch(0, full);
+        load_batch(kBatch, full);
+        TL(blockIdx.x, 2);
+        count_batch(0, full);
+        hash_batch(kBatch, full);
+        count_batch(kBatch, full);
+    };
+    const bool full_seg = (seg_n == kIters * 32);  // warp-uniform: all 16 steps of the warp hold 32 points
+    if (full_seg) walk1(std::true_type{}); else walk1(std::false_type{});
     hi_key = (__syncthreads_or(hi_key & 1) ? 1 : 0) | (__syncthreads_or(hi_key & 2) ? 2 : 0);  // (the intrinsic ORs predicates)
     TL(blockIdx.x, 3);
     if (tid < 2) s_runs[tid] = 0;
@@ -499,7 +511,8 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
         if (tid == 0) ws.tile_hi[loc.b] = (hi_key & 1) | (direct << 1);
     }
     // ---- walk 2: rank = earlier chunks + earlier warps + rank in segment; scatter the survivors ---------------------
-    if (open_keys) {
+    auto walk2 = [&](auto full) {
+        constexpr bool kFull = decltype(full)::value;
         // pass A: ranks (registers + shared memory only); pk[j] becomes key | rank << 13 for survivors, -1 otherwise.
         // Same-key lanes of a step own their ranks in arbitrary order, which only matters in the one step where the key
         // crosses M: those steps are found with ONE warp vote for the whole chunk and re-ranked in lane (= index) order.
@@ -508,7 +521,7 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
         unsigned cross = 0;
 #pragma unroll
         for (int j = 0; j < kIters; ++j) {
-            if (j * 32 < seg_n) {  // warp-uniform
+            if (kFull || j * 32 < seg_n) {  // warp-uniform
                 const int kj = pk[j] < 0 ? -1 : (pk[j] & ((1 << kKeyBits) - 1));
                 const int old = (pk[j] >> kKeyBits) & (int)kCntMask, rnd = (pk[j] >> (kKeyBits + kOldBits)) & 31;
                 const int act = kj >= 0 ? 1 : 0;
@@ -542,9 +555,8 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
         for (int j0 = 0; j0 < kIters; j0 += kBatch) {
 #pragma unroll
             for (int jj = 0; jj < kBatch; ++jj) {
-                const int i = (j0 + jj) * 32 + lane;
                 if (pk[j0 + jj] >= 0) {
-                    const float* p = seg_pts + (size_t)i * stride;
+                    const float* p = lane_pts + (size_t)((j0 + jj) * 32) * stride;
                     px[jj] = __ldg(p); py[jj] = __ldg(p + 1); pz[jj] = __ldg(p + 2);
                 }
             }
@@ -558,6 +570,9 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
                 }
             }
         }
+    };
+    if (open_keys) {
+        if (full_seg) walk2(std::true_type{}); else walk2(std::false_type{});
     }
     // ---- the last CTA of the tile to get here plans the tile ------------------------------------------------------------
     TL(blockIdx.x, 8);
