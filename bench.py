@@ -112,7 +112,9 @@ class ClockSampler:
             self.nvml = None
 
     def sample(self):
-        """One NVML reading; also called inline from the timed loop (the polling thread can starve behind the GIL)."""
+        """One NVML reading (polling thread; it runs while the main thread waits in the closing synchronize of the timed
+        region, i.e. while the queued steps execute -- an inline call from the launch loop would stall the launches: an
+        NVML query takes milliseconds)."""
         n = self.nvml
         if n is None:
             return
@@ -338,13 +340,8 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    # up to three inline readings (an NVML call takes about a millisecond: only while the device has that much work
-    # queued behind it, so the timed region never waits for the host)
-    inline = {args.steps // 4, args.steps // 2, (3 * args.steps) // 4} if args.steps >= 64 else set()
     for i in range(args.steps):
         run_step(i)
-        if i in inline:
-            sampler.sample()
     e1.record()
     barrier()
     clocks = sampler.stop()

@@ -350,6 +350,7 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
     auto hash_batch = [&](int j0, auto full) {
         constexpr bool kFull = decltype(full)::value;
         unsigned edge_bits = 0;  // points on the x / y max face (rare: one vote per batch, flags set on a slow path)
+        int kmax = -1;
 #pragma unroll
         for (int jj = 0; jj < kBatch; ++jj) {
             const int j = j0 + jj, i = j * 32 + lane;
@@ -359,10 +360,11 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
                 const int k = point_key<!kFast>(g, px[jj], py[jj], pz[jj], on_edge);  // (kFast: the launcher checked the overflow flag)
                 pk[j] = k;
                 edge_bits |= on_edge ? (1u << j) : 0u;
-                hi_key |= ((k >= g.num_cells) ? 1 : 0) | (on_edge ? 3 : 0);
+                kmax = k > kmax ? k : kmax;
                 if (!kFast && point_hash) point_hash[seg0 + i] = k;
             }
         }
+        hi_key |= ((kmax >= g.num_cells) ? 1 : 0) | (edge_bits ? 3 : 0);
         if (__any_sync(0xffffffffu, edge_bits != 0)) {
 #pragma unroll
             for (int jj = 0; jj < kBatch; ++jj)
@@ -445,16 +447,26 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
             const uint4* src = reinterpret_cast<const uint4*>(ws.chunk_hist + (size_t)loc.gstart * Kp) + k8;
             const size_t row = (size_t)Kp / 8;
             const uint4* rp = src;
-            for (int c0 = 0; c0 < loc.c; c0 += 8, rp += 8 * row) {
-                uint4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (c0 + u < loc.c) ? __ldcg(rp + u * row) : make_uint4(0, 0, 0, 0);
+            auto add_rows = [&](const uint4 (&v)[8]) {
                 // 8 rows of 16-bit counts (<= 4096 each) add up inside their 16-bit lanes without a carry
                 uint4 sum = v[0];
 #pragma unroll
                 for (int u = 1; u < 8; ++u) { sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w; }
                 acc[0] += sum.x & 0xFFFFu; acc[1] += sum.x >> 16; acc[2] += sum.y & 0xFFFFu; acc[3] += sum.y >> 16;
                 acc[4] += sum.z & 0xFFFFu; acc[5] += sum.z >> 16; acc[6] += sum.w & 0xFFFFu; acc[7] += sum.w >> 16;
+            };
+            int c0 = 0;
+            for (; c0 + 8 <= loc.c; c0 += 8, rp += 8 * row) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(rp + u * row);
+                add_rows(v);
+            }
+            if (c0 < loc.c) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (c0 + u < loc.c) ? __ldcg(rp + u * row) : make_uint4(0, 0, 0, 0);
+                add_rows(v);
             }
         }
 #pragma unroll
@@ -513,7 +525,7 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
     // ---- walk 2: rank = earlier chunks + earlier warps + rank in segment; scatter the survivors ---------------------
     auto walk2 = [&](auto full) {
         constexpr bool kFull = decltype(full)::value;
-        // pass A: ranks (registers + shared memory only); pk[j] becomes key | rank << 13 for survivors, -1 otherwise.
+        // pass A: ranks (registers + shared memory only); pk[j] becomes key | rank << 13 | group position << 24 (-1: no key).
         // Same-key lanes of a step own their ranks in arbitrary order, which only matters in the one step where the key
         // crosses M: those steps are found with ONE warp vote for the whole chunk and re-ranked in lane (= index) order.
         const uint32_t prefix_sa = smem_u32(prefix_s);
@@ -536,17 +548,21 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
             }
         }
         cross = __reduce_or_sync(0xffffffffu, cross);
+        if (cross) {  // warp-uniform; about 1 % of the steps are flagged
 #pragma unroll
-        for (int j = 0; j < kIters; ++j) {
-            const int kj = pk[j] < 0 ? -1 : (pk[j] & ((1 << kKeyBits) - 1));
-            unsigned rank = (unsigned)(pk[j] >> kKeyBits) & ((1u << kRankBits) - 1u);
-            if (cross & (1u << j)) {  // warp-uniform, about 1 % of the steps
-                const unsigned rnd = (unsigned)(pk[j] >> (kKeyBits + kRankBits)) & 31u;
-                const unsigned m = __match_any_sync(0xffffffffu, kj);
-                // lanes of a run whose first count lies below M (the others keep a rank >= M)
-                if (kj >= 0 && rank - rnd < (unsigned)M) rank = rank - rnd + (unsigned)__popc(m & ((1u << lane) - 1u));
+            for (int j = 0; j < kIters; ++j) {
+                if (cross & (1u << j)) {
+                    const int kj = pk[j] < 0 ? -1 : (pk[j] & ((1 << kKeyBits) - 1));
+                    unsigned rank = (unsigned)(pk[j] >> kKeyBits) & ((1u << kRankBits) - 1u);
+                    const unsigned rnd = (unsigned)(pk[j] >> (kKeyBits + kRankBits)) & 31u;
+                    const unsigned m = __match_any_sync(0xffffffffu, kj);
+                    // lanes of a run whose first count lies below M (the others keep a rank >= M)
+                    if (kj >= 0 && rank - rnd < (unsigned)M) {
+                        rank = rank - rnd + (unsigned)__popc(m & ((1u << lane) - 1u));
+                        pk[j] = kj | (int)(rank << kKeyBits);
+                    }
+                }
             }
-            pk[j] = (kj >= 0 && rank < (unsigned)M) ? (kj | (int)(rank << kKeyBits)) : -1;
         }
         TL(blockIdx.x, 7);
         // pass B: survivors re-read their xyz (L1 / L2 hits), all loads of a batch in flight before the first store
@@ -555,6 +571,8 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
         for (int j0 = 0; j0 < kIters; j0 += kBatch) {
 #pragma unroll
             for (int jj = 0; jj < kBatch; ++jj) {
+                // survivors: a key and a (provisional or re-ranked) rank below M
+                if (pk[j0 + jj] >= 0 && (((unsigned)pk[j0 + jj] >> kKeyBits) & ((1u << kRankBits) - 1u)) >= (unsigned)M) pk[j0 + jj] = -1;
                 if (pk[j0 + jj] >= 0) {
                     const float* p = lane_pts + (size_t)((j0 + jj) * 32) * stride;
                     px[jj] = __ldg(p); py[jj] = __ldg(p + 1); pz[jj] = __ldg(p + 2);
@@ -564,7 +582,7 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
             for (int jj = 0; jj < kBatch; ++jj) {
                 const int j = j0 + jj, i = j * 32 + lane;
                 if (pk[j] >= 0) {
-                    const int kj = pk[j] & ((1 << kKeyBits) - 1), rank = pk[j] >> kKeyBits;
+                    const int kj = pk[j] & ((1 << kKeyBits) - 1), rank = (pk[j] >> kKeyBits) & ((1 << kRankBits) - 1);
                     tile_slots[(size_t)kj * M + rank] =
                         make_float4(px[jj], py[jj], pz[jj], __int_as_float((int)(seg0 + i - loc.tile_start)));
                 }
