@@ -150,9 +150,10 @@ static int run_pfn(const PfnArgs& a, int precision, cudaStream_t st) {
     if (precision == P3P_PRECISION_FP32) return launch_pfn_simt(a, st);
     if (precision != P3P_PRECISION_TF32 && precision != P3P_PRECISION_BF16 && precision != P3P_PRECISION_FP16)
         return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
-    // The tensor-core kernel covers the shipped encoder configs (M = 64, C <= 384); other shapes of the density
-    // ablation take the exact-fp32 kernel, which is at least as accurate as either tensor-core contract.
-    if (a.g.M == 64 && a.bl.MT <= 3) return launch_pfn_tc(a, precision, st);
+    // The tensor-core kernel covers the shipped encoder configs and the low half of the density ablation (M <= 64: a
+    // pillar always takes 64 operand rows, C <= 384); M > 64 takes the exact-fp32 kernel, which is at least as accurate
+    // as either tensor-core contract.
+    if (a.g.M <= 64 && a.bl.MT <= 3) return launch_pfn_tc(a, precision, st);
     return launch_pfn_simt(a, st);
 }
 

@@ -13,7 +13,7 @@
 //         = relu(max_p(W1a' h_p) + W1b' hmax + b1)  (relu and "+ const" are monotone; the BN scale is already
 //                                                    inside W1a', so its sign does not matter)
 //
-// pfn_tc_kernel (M == 64, C <= 384): persistent warp-specialised pipeline, described at the kernel.
+// pfn_tc_kernel (M <= 64, C <= 384): persistent warp-specialised pipeline, described at the kernel.
 // The decorated (V, M, 8) tensor and every (V, M, *) intermediate of the reference never exist in HBM.
 //
 // pfn_simt_kernel: exact fp32 FMA, literal 8-channel formulation, any M and C -- the GPU-side cross-check of the
@@ -156,40 +156,51 @@ __device__ __forceinline__ int64_t out_index(const PfnArgs& a, int64_t item, int
 // ------------------------------------------------------------------------------------------------
 // exact fp32 kernel (literal formulation)
 // ------------------------------------------------------------------------------------------------
-constexpr int kSimtThreads = 128;
+constexpr int kSimtMaxThreads = 512;
 constexpr int kHStride = 36;  // floats per H row: 16-byte aligned and bank-conflict free for float4 row stores
 
-__global__ void __launch_bounds__(kSimtThreads) pfn_simt_kernel(PfnArgs a) {
+// One CTA per work item at a time, thread = output channel (blockDim = C rounded up to a warp, C <= 512): the channel's 64
+// folded layer-1 weights stay in registers for every item of the CTA, the pillar's layer-0 rows sit in shared memory.
+// kHoist = false (C > 512): threads loop over channels and re-read their weights per item.
+template <bool kHoist>
+__global__ void __launch_bounds__(kSimtMaxThreads) pfn_simt_kernel(PfnArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     float* H = smem_f;                                  // [(M + 1)][kHStride]
     float* w0s = H + (size_t)(a.g.M + 1) * kHStride;    // [32][8]
     float* b0s = w0s + 256;                             // [32]
-    int* red = reinterpret_cast<int*>(b0s + 32);        // [4][6] fixed-point partial sums
-    int* hmax_bits = red + 24;                          // [32]
+    int* red = reinterpret_cast<int*>(b0s + 32);        // [16 warps][6] fixed-point partial sums
+    int* hmax_bits = red + 96;                          // [32]
 
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
     const float* w0g = reinterpret_cast<const float*>(a.blob + a.bl.off_w0);
     const float* b0g = reinterpret_cast<const float*>(a.blob + a.bl.off_b0);
     const float* w1g = reinterpret_cast<const float*>(a.blob + a.bl.off_w1);
     const float* b1g = reinterpret_cast<const float*>(a.blob + a.bl.off_b1);
     const int alias = reinterpret_cast<const int*>(a.blob + a.bl.off_header)[4];
-    for (int i = tid; i < 256; i += kSimtThreads) w0s[i] = w0g[i];
+    for (int i = tid; i < 256; i += nthreads) w0s[i] = w0g[i];
     if (tid < 32) b0s[tid] = b0g[tid];
-    __syncthreads();
     const int C = a.bl.C, M = a.g.M;
+    float wa[32], wb[32], b1c = 0.f;
+    if (kHoist) {
+        const int c = tid < C ? tid : 0;
+        b1c = b1g[c];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { wa[k] = w1g[(size_t)c * 64 + k]; wb[k] = w1g[(size_t)c * 64 + 32 + k]; }
+    }
+    __syncthreads();
 
     for (int64_t item = blockIdx.x; item < a.num_items; item += gridDim.x) {
         const Item it = fetch_item(a, item);
         if (!it.valid) {
             if (a.item_mode == kItemsCanvas)
-                for (int c = tid; c < C; c += kSimtThreads) store_scalar(a, out_index(a, item, it.b, it.cell, c), 0.f);
+                for (int c = tid; c < C; c += nthreads) store_scalar(a, out_index(a, item, it.b, it.cell, c), 0.f);
             continue;
         }
         const float4* slot = item_slots(a, it);
         const int n = it.n;
         // cluster mean over the kept points (padded slots are zeros in the reference's sum), on the fixed-point grid
         int sl[3] = {0, 0, 0}, sh[3] = {0, 0, 0};
-        for (int r = tid; r < n; r += kSimtThreads) {
+        for (int r = tid; r < n; r += nthreads) {
             const float4 p = slot[r];
             int lo, hi;
             fix_split(p.x, a.g.fix_scale, lo, hi); sl[0] += lo; sh[0] += hi;
@@ -204,15 +215,22 @@ __global__ void __launch_bounds__(kSimtThreads) pfn_simt_kernel(PfnArgs a) {
         }
         if (tid < 32) hmax_bits[tid] = 0;
         __syncthreads();
+        int tl[3] = {0, 0, 0}, th[3] = {0, 0, 0};
+        for (int ww = 0; ww < nwarps; ++ww) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { tl[i] += red[ww * 6 + i]; th[i] += red[ww * 6 + 3 + i]; }
+        }
         const float fn = (float)n;
-        const float mx = fix_mean(red[0] + red[6] + red[12] + red[18], red[3] + red[9] + red[15] + red[21], a.g.fix_inv, fn);
-        const float my = fix_mean(red[1] + red[7] + red[13] + red[19], red[4] + red[10] + red[16] + red[22], a.g.fix_inv, fn);
-        const float mz = fix_mean(red[2] + red[8] + red[14] + red[20], red[5] + red[11] + red[17] + red[23], a.g.fix_inv, fn);
+        const float mx = fix_mean(tl[0], th[0], a.g.fix_inv, fn);
+        const float my = fix_mean(tl[1], th[1], a.g.fix_inv, fn);
+        const float mz = fix_mean(tl[2], th[2], a.g.fix_inv, fn);
 
         float hm[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) hm[k] = 0.f;
-        for (int r = tid; r < n; r += kSimtThreads) {
+        bool any_row = false;
+        for (int r = tid; r < n; r += nthreads) {
+            any_row = true;
             const float4 p = slot[r];
             float d[8];
             const float xc = p.x - it.ctr_x, yc = p.y - it.ctr_y;
@@ -230,10 +248,12 @@ __global__ void __launch_bounds__(kSimtThreads) pfn_simt_kernel(PfnArgs a) {
                 hm[k] = fmaxf(hm[k], h);
             }
         }
+        if (__any_sync(0xffffffffu, any_row)) {  // (warp-uniform) warps without a row have nothing to contribute
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const float v = warp_max_f32(hm[k]);
-            if (lane == 0) atomicMax(&hmax_bits[k], __float_as_int(v));  // h >= 0: int order == float order
+            for (int k = 0; k < 32; ++k) {
+                const float v = warp_max_f32(hm[k]);
+                if (lane == 0) atomicMax(&hmax_bits[k], __float_as_int(v));  // h >= 0: int order == float order
+            }
         }
         if (n < M && tid < 32) {  // one representative padded slot: relu(BN(0))
             const float hp = fmaxf(b0s[tid], 0.f);
@@ -242,29 +262,51 @@ __global__ void __launch_bounds__(kSimtThreads) pfn_simt_kernel(PfnArgs a) {
         }
         __syncthreads();
         const int rows = n + (n < M ? 1 : 0);
-        for (int c = tid; c < C; c += kSimtThreads) {
-            float wa[32];
-            float g = b1g[c];
+        if (kHoist) {
+            if (tid < C) {
+                float g = b1c;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                wa[k] = w1g[(size_t)c * 64 + k];
-                g = __fmaf_rn(w1g[(size_t)c * 64 + 32 + k], __int_as_float(hmax_bits[k]), g);
-            }
-            float best = -INFINITY;
-            for (int r = 0; r < rows; ++r) {
-                const float4* hr = reinterpret_cast<const float4*>(H + (size_t)r * kHStride);
-                float acc = 0.f;
+                for (int k = 0; k < 32; ++k) g = __fmaf_rn(wb[k], __int_as_float(hmax_bits[k]), g);
+                float best = -INFINITY;
+                for (int r = 0; r < rows; ++r) {
+                    const float4* hr = reinterpret_cast<const float4*>(H + (size_t)r * kHStride);
+                    float acc = 0.f;
 #pragma unroll
-                for (int k4 = 0; k4 < 8; ++k4) {
-                    const float4 h = hr[k4];
-                    acc = __fmaf_rn(wa[k4 * 4 + 0], h.x, acc);
-                    acc = __fmaf_rn(wa[k4 * 4 + 1], h.y, acc);
-                    acc = __fmaf_rn(wa[k4 * 4 + 2], h.z, acc);
-                    acc = __fmaf_rn(wa[k4 * 4 + 3], h.w, acc);
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const float4 h = hr[k4];
+                        acc = __fmaf_rn(wa[k4 * 4 + 0], h.x, acc);
+                        acc = __fmaf_rn(wa[k4 * 4 + 1], h.y, acc);
+                        acc = __fmaf_rn(wa[k4 * 4 + 2], h.z, acc);
+                        acc = __fmaf_rn(wa[k4 * 4 + 3], h.w, acc);
+                    }
+                    best = fmaxf(best, acc);
                 }
-                best = fmaxf(best, acc);
+                store_scalar(a, out_index(a, item, it.b, it.cell, tid), fmaxf(best + g, 0.f));
             }
-            store_scalar(a, out_index(a, item, it.b, it.cell, c), fmaxf(best + g, 0.f));
+        } else {
+            for (int c = tid; c < C; c += nthreads) {
+                float g = b1g[c];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    wa[k] = w1g[(size_t)c * 64 + k];
+                    g = __fmaf_rn(w1g[(size_t)c * 64 + 32 + k], __int_as_float(hmax_bits[k]), g);
+                }
+                float best = -INFINITY;
+                for (int r = 0; r < rows; ++r) {
+                    const float4* hr = reinterpret_cast<const float4*>(H + (size_t)r * kHStride);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const float4 h = hr[k4];
+                        acc = __fmaf_rn(wa[k4 * 4 + 0], h.x, acc);
+                        acc = __fmaf_rn(wa[k4 * 4 + 1], h.y, acc);
+                        acc = __fmaf_rn(wa[k4 * 4 + 2], h.z, acc);
+                        acc = __fmaf_rn(wa[k4 * 4 + 3], h.w, acc);
+                    }
+                    best = fmaxf(best, acc);
+                }
+                store_scalar(a, out_index(a, item, it.b, it.cell, c), fmaxf(best + g, 0.f));
+            }
         }
         __syncthreads();
     }
@@ -380,7 +422,7 @@ __device__ __forceinline__ float max32(const float (&v)[32]) {
     return fmaxf(fmax3(fmax3(r[0], r[1], r[2]), fmax3(r[3], r[4], r[5]), fmax3(r[6], r[7], r[8])), fmaxf(r[9], r[10]));
 }
 
-// pfn_tc_kernel (M == 64, C <= 384): per CTA a persistent pipeline
+// pfn_tc_kernel (M <= 64, C <= 384): per CTA a persistent pipeline
 //   8 front-end warps  : warp w takes item w of every unit (8 consecutive items); layer 0 in its affine form
 //                        W0' d_p + b0 = Ux x' + Uy y' + Uz z + kappa(pillar)   (x' = x - centre_x, ...)
 //                        -> 3 FMA per (point, channel); 16-byte row chunks written (tf32 / 16-bit) straight into the
@@ -639,9 +681,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                 }
                 const uint32_t stage_sa = smem_u32(sH) + (uint32_t)st * Cfg::kHStage;
                 if constexpr (kTf32) {
+                    // rows beyond the pillar's n points: relu(BN(0)) of a padded slot while n < M; when the pillar is
+                    // full at M < 64 the reference has no padded slot, the spare rows repeat slot 0 (the max ignores them)
                     float hp[8], mx8[8];
+                    if (n < a.g.M || n == 64) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) { hp[c] = kc[9 * 32 + c]; mx8[c] = (n < 64) ? hp[c] : 0.f; }
+                        for (int c = 0; c < 8; ++c) hp[c] = kc[9 * 32 + c];
+                    } else {
+                        const float4 q0 = P[0];
+                        const float x0 = q0.x - it.ctr_x, y0 = q0.y - it.ctr_y, z0 = q0.z;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float2 v = ffma2(ux[c], make_float2(x0, x0), ffma2(uy[c], make_float2(y0, y0), ffma2(uz[c], make_float2(z0, z0), kap[c])));
+                            hp[2 * c] = fmaxf(v.x, 0.f); hp[2 * c + 1] = fmaxf(v.y, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) mx8[c] = (n < 64) ? hp[c] : 0.f;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         float h[8];
@@ -684,9 +740,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                             sts128(stage_sa + row_off[0] + (uint32_t)i * (8u * Cfg::RB), h[0], h[1], h[2], h[3]);
                         }
                     } else {
+                        // rows beyond the pillar's n points: relu(BN(0)) of a padded slot while n < M; when the pillar
+                        // is full at M < 64 the reference has no padded slot, the spare rows repeat slot 0
                         uint32_t hp[4];
+                        if (n < a.g.M) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) hp[c] = pack_relu16<kPrec>(kc[9 * 32 + 2 * c], kc[9 * 32 + 2 * c + 1]);
+                            for (int c = 0; c < 4; ++c) hp[c] = pack_relu16<kPrec>(kc[9 * 32 + 2 * c], kc[9 * 32 + 2 * c + 1]);
+                        } else {
+                            const float4 q0 = P[0];
+                            const float x0 = q0.x - it.ctr_x, y0 = q0.y - it.ctr_y, z0 = q0.z;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float2 v = ffma2(ux[c], make_float2(x0, x0), ffma2(uy[c], make_float2(y0, y0), ffma2(uz[c], make_float2(z0, z0), kap[c])));
+                                hp[c] = pack_relu16<kPrec>(v.x, v.y);
+                            }
+                        }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             uint32_t h[4];
@@ -822,16 +890,22 @@ int launch_pfn_prepare(const p3p_pfn_params* p, int precision, char* blob, const
 int launch_pfn_simt(const PfnArgs& a, cudaStream_t st) {
     if (a.num_items <= 0) return P3P_OK;
     if (a.num_items > 0x7fffffff - 64) return fail(P3P_ERR_UNSUPPORTED, "%lld work items exceed the 32-bit item index", (long long)a.num_items);
-    const size_t smem = ((size_t)(a.g.M + 1) * kHStride + 256 + 32 + 24 + 32) * sizeof(float);
+    const size_t smem = ((size_t)(a.g.M + 1) * kHStride + 256 + 32 + 96 + 32) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
-        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
     }
     const int sms = device_sm_count();
-    int64_t grid = (int64_t)sms * 8;
+    const bool hoist = a.bl.C <= kSimtMaxThreads;
+    const int threads = hoist ? (a.bl.C + 31) / 32 * 32 : kSimtMaxThreads;
+    int64_t grid = (int64_t)sms * (hoist ? (threads <= 256 ? 4 : 2) : 2);
     if (grid > a.num_items) grid = a.num_items;
-    pfn_simt_kernel<<<(unsigned)grid, kSimtThreads, smem, st>>>(a);
+    if (hoist)
+        pfn_simt_kernel<true><<<(unsigned)grid, threads, smem, st>>>(a);
+    else
+        pfn_simt_kernel<false><<<(unsigned)grid, threads, smem, st>>>(a);
     P3P_CUDA_CHECK(cudaGetLastError());
     return P3P_OK;
 }
