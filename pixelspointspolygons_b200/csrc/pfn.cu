@@ -334,6 +334,10 @@ constexpr int kMmaWarps = 4;                   // warp group 0: warp m < 3 issue
 constexpr int kEpiWarp0 = kMmaWarps + kNF;     // then kNF front-end warps, then the epilogue warps
 constexpr int kEpiGroups = 3;                  // epilogue groups of 4 warps (one warp per TMEM lane quarter)
 constexpr int kTcThreads = 32 * (kEpiWarp0 + 4 * kEpiGroups);
+#ifndef P3P_NS_16
+#define P3P_NS_16 8
+#define P3P_NS_TF32 4
+#endif
 #ifndef P3P_REG_MMA
 #define P3P_REG_MMA 40
 #define P3P_REG_FRONT 120
@@ -358,7 +362,7 @@ struct TcCfg {
     static constexpr uint32_t kLayout = kTf32 ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
     static constexpr uint32_t kSBO = 8 * RB;
     static constexpr int kKSteps = kTf32 ? 4 : 2;         // UMMA_K = 8 (tf32) / 16 (16-bit): 32 bytes per step
-    static constexpr int kNS = kTf32 ? 4 : 8;             // B-operand stages: pillar pairs in flight
+    static constexpr int kNS = kTf32 ? P3P_NS_TF32 : P3P_NS_16;            // B-operand stages: pillar pairs in flight
     static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * kHStage;
     static constexpr size_t kSmemFloats = 10 * 32 + 384 + kNF * 128 * 4;
     static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + (2 * kNS + 2 * kTmemStages + 2) * 8 + 16 + 2 * kNF * 4 + 2 * kValidRing;
