@@ -229,6 +229,26 @@ def test_full_size_batch_properties(cuda_device):
     assert raw["num_pillars"].max() <= 784
 
 
+def test_multi_wave_batch_with_dependent_launch(cuda_device):
+    """40 tiles x 60k points = about 1000 ranking chunks, more than two waves of the voxelizer grid: the PFN grid is a
+    programmatic dependent launch that may start while the voxelizer's last wave drains -- no deadlock, same results."""
+    grid = po.GridSpec()
+    enc, ref = build(cuda_device, grid, seed=12)
+    tiles = [po.synth_tile(60_000, 3000 + i, clustered=(i % 3 == 0)) for i in range(40)]
+    x = to_nested(tiles, cuda_device)
+    with torch.no_grad():
+        out = enc(x)
+        torch.cuda.synchronize()
+        for _ in range(3):  # back to back: the next voxelizer follows the dependent launch of the previous step
+            again = enc(x)
+        torch.cuda.synchronize()
+        assert torch.equal(out, again)
+        sub = enc(to_nested(tiles[37:40], cuda_device))
+        assert torch.equal(sub, out[37:40])
+        r = ref(tiles[38:40])
+    assert_close(out[38:40], r, 1e-3, "multi-wave batch")
+
+
 def test_training_path_runs_and_matches_train_mode_oracle(cuda_device):
     grid = po.GridSpec()
     enc, ref = build(cuda_device, grid, seed=11)
