@@ -340,8 +340,8 @@ constexpr int kTcThreads = 32 * (kEpiWarp0 + 4 * kEpiGroups);
 #endif
 #ifndef P3P_REG_MMA
 #define P3P_REG_MMA 40
-#define P3P_REG_FRONT 120
-#define P3P_REG_EPI 64
+#define P3P_REG_FRONT 112
+#define P3P_REG_EPI 72
 #endif
 constexpr int kRegMma = P3P_REG_MMA, kRegFront = P3P_REG_FRONT, kRegEpi = P3P_REG_EPI;  // registers per thread after setmaxnreg (launch: 80)
 static_assert(4 * kRegMma + 8 * kRegFront + 12 * kRegEpi <= 24 * 80, "register pool of the launch exceeded");
@@ -350,7 +350,7 @@ constexpr int kPairsPerUnit = kUnit / 2;
 constexpr int kTmemStage = 144;                // TMEM columns per accumulator stage: 128 (pillar pair) + 16 (W1b' hmax of the pair)
 constexpr int kTmemStages = 3;                 // ring of accumulator stages shared by the epilogue groups
 constexpr int kValidRing = 64;               // pairs of validity flags in flight between front end and epilogue (>= kNS + ring slack)
-constexpr int kStageRows = 144;                // operand rows of a pair: 2 x 64 slots + the 2 hmax rows (padded to 16)
+constexpr int kStageRows = 128;                // operand rows of a pair: 2 x 64 slots
 
 template <int kPrec>
 struct TcCfg {
@@ -358,14 +358,15 @@ struct TcCfg {
     static constexpr int kFmt = kTf32 ? 2 : (kPrec == P3P_PRECISION_BF16 ? 1 : 0);  // UMMA operand format code
     static constexpr int RB = kTf32 ? 128 : 64;           // bytes of one K = 32 operand row
     static constexpr int kATile = 128 * RB;               // 128 channels
-    static constexpr int kHStage = kStageRows * RB;       // 2 pillars x 64 rows + 16 hmax rows
+    static constexpr int kHStage = kStageRows * RB;       // 2 pillars x 64 rows
+    static constexpr int kGStage = 16 * RB;               // hmax rows of the 8 items of a unit (padded to 16)
     static constexpr uint32_t kLayout = kTf32 ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
     static constexpr uint32_t kSBO = 8 * RB;
     static constexpr int kKSteps = kTf32 ? 4 : 2;         // UMMA_K = 8 (tf32) / 16 (16-bit): 32 bytes per step
     static constexpr int kNS = kTf32 ? P3P_NS_TF32 : P3P_NS_16;            // B-operand stages: pillar pairs in flight
-    static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * kHStage;
+    static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * kHStage + 2 * (size_t)kGStage;
     static constexpr size_t kSmemFloats = 10 * 32 + 384 + kNF * 128 * 4;
-    static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + (2 * kNS + 2 * kTmemStages + 2) * 8 + 16 + 2 * kNF * 4 + 2 * kValidRing;
+    static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + (2 * kNS + 4 * kTmemStages + 2 + 2) * 8 + 16 + 2 * kNF * 4 + 2 * kValidRing;
 };
 
 
@@ -418,6 +419,14 @@ struct ItemWalk {
     }
 };
 
+__device__ __forceinline__ void tmem_ld8_wait(uint32_t taddr, float (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ float max32(const float (&v)[32]) {
     float r[11];
 #pragma unroll
@@ -431,8 +440,8 @@ __device__ __forceinline__ float max32(const float (&v)[32]) {
 //                        W0' d_p + b0 = Ux x' + Uy y' + Uz z + kappa(pillar)   (x' = x - centre_x, ...)
 //                        -> 3 FMA per (point, channel); 16-byte row chunks written (tf32 / 16-bit) straight into the
 //                        swizzled K-major B-operand stage of the pair, hmax into the stage's two extra rows
-//   3 MMA warps        : warp m, per pair: D[128 ch x 2 x 64 pts] = W1a'[tile m] H^T and D[128 ch x 16] = W1b'[tile m] hmax^T
-//                        into accumulator stage m (one elected thread issues)
+//   3 MMA warps        : warp m, per pair: D[128 ch x 128 pts] = W1a'[tile m] H^T into accumulator stage m; per unit
+//                        (8 items): D[128 ch x 16] = W1b'[tile m] hmax^T into the stage's 16 spare columns
 //   3 x 4 epilogue warps: group g reads accumulator stage g: tcgen05.ld, max over each
 //                        pillar's 64 columns with 3-input max, + W1b' hmax + b1, relu, store of the two cells.
 // kMode: 0 = any item source / layout / dtype (run-time branches); 1 = canvas items, whole units inside one tile, fp32 rows
@@ -448,8 +457,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     unsigned char* base = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
     unsigned char* sA1 = base;
     unsigned char* sA2 = sA1 + 3 * Cfg::kATile;
-    unsigned char* sH = sA2 + 3 * Cfg::kATile;                          // [kNS][144 rows]
-    float* sFront = reinterpret_cast<float*>(sH + kNS * Cfg::kHStage);  // [10][32]
+    unsigned char* sH = sA2 + 3 * Cfg::kATile;                          // [kNS][128 rows]
+    unsigned char* sG = sH + kNS * Cfg::kHStage;                        // [2 unit slots][16 rows]: hmax rows of a unit's 8 items
+    float* sFront = reinterpret_cast<float*>(sG + 2 * Cfg::kGStage);    // [10][32]
     float* sB1 = sFront + 10 * 32;                                      // [384]
     float4* sPts = reinterpret_cast<float4*>(sB1 + 384);                // [kNF][2 sets][64] points of the pillar in work / of the next one
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPts + kNF * 128);
@@ -457,7 +467,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     uint64_t* h_empty = bars + kNS;           // [kNS] MMA -> front end (one tcgen05.commit per channel tile)
     uint64_t* t_full = bars + 2 * kNS;        // [3] MMA warp m -> epilogue group m (tcgen05.commit), per pair
     uint64_t* t_empty = t_full + kTmemStages; // [3] epilogue group m -> MMA warp m (128 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + kTmemStages);
+    uint64_t* gt_full = t_empty + kTmemStages;  // [3] MMA warp m -> epilogue group m, per unit (W1b' hmax accumulator)
+    uint64_t* gt_empty = gt_full + kTmemStages; // [3] epilogue group m -> MMA warp m (128 arrivals)
+    uint64_t* g_empty = gt_empty + kTmemStages; // [2] MMA warps -> front end: hmax rows of the unit slot consumed (MT commits)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_empty + 2);
     int* sDesc = reinterpret_cast<int*>(tmem_slot + 2);                 // [kNF][2] descriptor word of the item decoded next
     unsigned char* sValid = reinterpret_cast<unsigned char*>(sDesc + 2 * kNF);  // [kValidRing pairs][2]: the item holds a pillar
 
@@ -473,7 +486,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
         for (int i = 0; i < kNS; ++i) { mbar_init(&h_full[i], 2); mbar_init(&h_empty[i], (uint32_t)MT); }
-        for (int i = 0; i < kTmemStages; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
+        for (int i = 0; i < kTmemStages; ++i) {
+            mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128);
+            mbar_init(&gt_full[i], 1); mbar_init(&gt_empty[i], 128);
+        }
+        mbar_init(&g_empty[0], (uint32_t)MT); mbar_init(&g_empty[1], (uint32_t)MT);
         fence_mbar_init();
     }
     {
@@ -484,11 +501,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             reinterpret_cast<uint4*>(sA1)[i] = g1[i];
             reinterpret_cast<uint4*>(sA2)[i] = g2[i];
         }
-        // the 14 unused hmax rows of every stage feed accumulator columns nobody reads; zero them once all the same
-        for (int i = tid; i < kNS * 16 * Cfg::RB / 16; i += kTcThreads) {
-            const int st = i / (16 * Cfg::RB / 16), o = i - st * (16 * Cfg::RB / 16);
-            reinterpret_cast<uint4*>(sH + (size_t)st * Cfg::kHStage + 128 * Cfg::RB)[o] = make_uint4(0, 0, 0, 0);
-        }
+        // rows 8..15 of the hmax blocks feed accumulator columns nobody reads; zero the blocks once all the same
+        for (int i = tid; i < 2 * Cfg::kGStage / 16; i += kTcThreads) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0, 0, 0, 0);
         const float* fg = reinterpret_cast<const float*>(a.blob + a.bl.off_front);
         const float* b1g = reinterpret_cast<const float*>(a.blob + a.bl.off_b1);
         for (int i = tid; i < 10 * 32; i += kTcThreads) sFront[i] = fg[i];
@@ -504,8 +518,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
 
     // Register budget per role (warp groups of 4 warps): the launch allots 80 registers per thread; the issuers and the
     // epilogue hand registers back, the front end (long independent FMA chains) takes them.  Measured splits
-    // (MMA / front / epilogue -> fp16, tf32 kernel time): 40/112/72 -> 43.3, 68.9 us; 40/120/64 -> 43.9, 52.4 us;
-    // 40/136/56 -> 44.6, 53.1 us; 24/104/80 -> 78.6, 55.2 us (the issuers spill below 32); no reallocation -> 47.1, 56.4 us.
+    // (MMA / front / epilogue -> fp16, tf32 kernel time), per-pair W1b'hmax MMA: 40/112/72 -> 43.3, 68.9 us; 40/120/64 ->
+    // 43.9, 52.4 us; 40/136/56 -> 44.6, 53.1 us; 24/104/80 -> 78.6, 55.2 us (the issuers spill below 32); no reallocation
+    // -> 47.1, 56.4 us.  With the per-unit W1b'hmax MMA (the epilogue holds a unit's 8 maxima): 40/120/64 -> 45.0, 52.2 us;
+    // 40/112/72 -> 39.6, 50.9 us.
     if (warp < kMmaWarps) {
         setmaxnreg_dec<kRegMma>();
         // =========================== MMA issuers: warp m owns channel tile m and accumulator stage m ===========================
@@ -520,7 +536,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             const uint32_t desc_hi = (Cfg::kSBO >> 4) | (1u << 14) | (Cfg::kLayout << 29);
             const uint32_t a1_lo = ((smem_u32(sA1) + (uint32_t)(m * Cfg::kATile)) >> 4) | (1u << 16);
             const uint32_t a2_lo = ((smem_u32(sA2) + (uint32_t)(m * Cfg::kATile)) >> 4) | (1u << 16);
-            const uint32_t h_lo = (smem_u32(sH) >> 4) | (1u << 16);
+            const uint32_t h_lo = (smem_u32(sH) >> 4) | (1u << 16), g_lo = (smem_u32(sG) >> 4) | (1u << 16);
             const uint32_t d_main = tmem_base + (uint32_t)(m * kTmemStage);
             int st = 0;
             uint32_t use = 0;
@@ -529,7 +545,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                 if (m == 0) PTL(0, p, 0);
                 tc_fence_after();
                 const uint32_t hs_lo = h_lo + (uint32_t)st * (Cfg::kHStage >> 4);
-                const uint32_t gs_lo = hs_lo + (uint32_t)((128 * Cfg::RB) >> 4);
                 {
                     mbar_wait(&t_empty[m], ((uint32_t)p & 1u) ^ 1u);
                     if (m == 0) PTL(0, p, 1);
@@ -539,10 +554,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                         for (int k = 0; k < Cfg::kKSteps; ++k)
                             tc_mma<kTf32>(d_main, ((uint64_t)desc_hi << 32) | (a1_lo + (uint32_t)(k * 2)),
                                           ((uint64_t)desc_hi << 32) | (hs_lo + (uint32_t)(k * 2)), idesc_main, k > 0);
-#pragma unroll
-                        for (int k = 0; k < Cfg::kKSteps; ++k)
-                            tc_mma<kTf32>(d_main + 128, ((uint64_t)desc_hi << 32) | (a2_lo + (uint32_t)(k * 2)),
-                                          ((uint64_t)desc_hi << 32) | (gs_lo + (uint32_t)(k * 2)), idesc_g, k > 0);
                         tc_commit(&t_full[m]);
                     }
                     __syncwarp();
@@ -551,6 +562,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                 __syncwarp();
                 if (m == 0) PTL(0, p, 2);
                 if (++st == kNS) { st = 0; ++use; }
+                // ---- end of a unit (all 8 hmax rows are written: its 4 pairs have arrived): W1b' hmax of the 8 items
+                //      with one N = 16 MMA chain into the tile's 16 spare accumulator columns -----------------------------
+                if ((p & (kPairsPerUnit - 1)) == kPairsPerUnit - 1) {
+                    const uint32_t j = (uint32_t)p / kPairsPerUnit, slot = j & 1u;
+                    mbar_wait(&gt_empty[m], (j & 1u) ^ 1u);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t gs_lo = g_lo + slot * (Cfg::kGStage >> 4);
+#pragma unroll
+                        for (int k = 0; k < Cfg::kKSteps; ++k)
+                            tc_mma<kTf32>(d_main + 128, ((uint64_t)desc_hi << 32) | (a2_lo + (uint32_t)(k * 2)),
+                                          ((uint64_t)desc_hi << 32) | (gs_lo + (uint32_t)(k * 2)), idesc_g, k > 0);
+                        tc_commit(&gt_full[m]);
+                        tc_commit(&g_empty[slot]);
+                    }
+                    __syncwarp();
+                }
             }
         }
     } else if (warp < kEpiWarp0) {
@@ -581,9 +609,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             row_off[0] = (uint32_t)(half * 64 + pt) * Cfg::RB + (uint32_t)((o ^ ((pt >> 1) & 3)) * 16);
             row_off[1] = 0;
         }
-        // hmax row (128 + half) of the stage: swizzle phase (row >> 1) & 3 = 0 (16-bit rows), row & 7 = half (tf32 rows)
-        const uint32_t g_off0 = (uint32_t)(128 + half) * Cfg::RB + (uint32_t)(kTf32 ? (((2 * o) ^ half) * 16) : (o * 16));
-        const uint32_t g_off1 = (uint32_t)(128 + half) * Cfg::RB + (uint32_t)(((2 * o + 1) ^ half) * 16);
+        // hmax row fw of the unit's block of 16 rows, the lane's chunk(s) under the swizzle
+        const uint32_t g_off0 = (uint32_t)fw * Cfg::RB + (uint32_t)(kTf32 ? (((2 * o) ^ (fw & 7)) * 16) : ((o ^ ((fw >> 1) & 3)) * 16));
+        const uint32_t g_off1 = (uint32_t)fw * Cfg::RB + (uint32_t)(((2 * o + 1) ^ (fw & 7)) * 16);
         const float inv_nx = 1.0f / (float)a.g.nx;
         auto item_of = [&](int j) -> int { return (j < my_units) ? ((int)blockIdx.x + j * (int)gridDim.x) * kUnit + fw : total_items; };
         // descriptor word of item j (canvas: cell_desc; list: resolved when decoded) travels through shared memory by
@@ -642,7 +670,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             const uint32_t use = (uint32_t)(p / kNS);
             PTL(1 + fw, j, 0);
             mbar_wait(&h_empty[st], (use & 1u) ^ 1u);
+            mbar_wait(&g_empty[j & 1], (((uint32_t)j >> 1) & 1u) ^ 1u);  // the unit slot's hmax rows of two units ago are consumed
             PTL(1 + fw, j, 1);
+            const uint32_t gslot_sa = smem_u32(sG) + (uint32_t)(j & 1) * Cfg::kGStage;
             if (it.valid) {
                 const int n = it.n;
                 const float4* P = pbuf + (j & 1) * 64;
@@ -726,8 +756,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                         for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(mx8[c], __shfl_xor_sync(0xffffffffu, mx8[c], off));
                     }
                     if (pt == 0) {
-                        sts128(stage_sa + g_off0, __float_as_uint(mx8[0]), __float_as_uint(mx8[1]), __float_as_uint(mx8[2]), __float_as_uint(mx8[3]));
-                        sts128(stage_sa + g_off1, __float_as_uint(mx8[4]), __float_as_uint(mx8[5]), __float_as_uint(mx8[6]), __float_as_uint(mx8[7]));
+                        sts128(gslot_sa + g_off0, __float_as_uint(mx8[0]), __float_as_uint(mx8[1]), __float_as_uint(mx8[2]), __float_as_uint(mx8[3]));
+                        sts128(gslot_sa + g_off1, __float_as_uint(mx8[4]), __float_as_uint(mx8[5]), __float_as_uint(mx8[6]), __float_as_uint(mx8[7]));
                     }
                 } else {
                     uint32_t mm[4] = {0u, 0u, 0u, 0u};
@@ -777,7 +807,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) mm[c] = max16x2<kPrec>(mm[c], __shfl_xor_sync(0xffffffffu, mm[c], off));
                     }
-                    if (pt == 0) sts128(stage_sa + g_off0, mm[0], mm[1], mm[2], mm[3]);
+                    if (pt == 0) sts128(gslot_sa + g_off0, mm[0], mm[1], mm[2], mm[3]);
                 }
             }
             if (lane == 0) sValid[(p & (kValidRing - 1)) * 2 + half] = (unsigned char)it.valid;
@@ -804,78 +834,91 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         ItemWalk wu;  // position of the first item of the unit in work
         wu.init((int)blockIdx.x * kUnit < total_items ? (int)blockIdx.x * kUnit : 0, (int)gridDim.x * kUnit, ipt);
         int unit_item0 = (int)blockIdx.x * kUnit;
+        const int m = g;  // group g reads accumulator stage g = channel tile g
+        const float bb = (m == 0) ? b1v[0] : ((m == 1) ? b1v[1] : b1v[2]);
+        const int c = m * 128 + cl;
+        const uint32_t taddr = tlane + (uint32_t)(g * kTmemStage);
         int jn = 0;
-        for (int p = 0; p < (g < MT ? my_pairs : 0); ++p) {
-            const int pr = p & (kPairsPerUnit - 1);
-            const int item = unit_item0 + 2 * pr;
+        for (int j = 0; j < (g < MT ? my_units : 0); ++j) {
             const int ub = wu.b, ur = wu.r;  // tile / position of the unit's first item
-            if (pr == kPairsPerUnit - 1) { wu.step(); unit_item0 += (int)gridDim.x * kUnit; }
-            {
-                const int m = g;  // group g reads accumulator stage g = channel tile g
-                const uint32_t ts = (uint32_t)g;
-                const uint32_t tph = (uint32_t)p & 1u;
-                const uint32_t taddr = tlane + ts * kTmemStage;
-                float va[32], vb[32], g0, g1;
+            const int item0 = unit_item0;
+            wu.step();
+            unit_item0 += (int)gridDim.x * kUnit;
+            // ---- the unit's 4 pairs: max over each pillar's 64 accumulator columns -----------------------------------
+            float rmax[kUnit];
+#pragma unroll
+            for (int pr = 0; pr < kPairsPerUnit; ++pr, ++jn) {
+                const uint32_t tph = (uint32_t)(j * kPairsPerUnit + pr) & 1u;
+                float va[32], vb[32];
                 if (quad == 0) PTL(9 + g, jn, 0);
-                mbar_wait(&t_full[ts], tph);
+                mbar_wait(&t_full[g], tph);
                 if (quad == 0) PTL(9 + g, jn, 1);
                 tc_fence_after();
                 tmem_ld32_wait(taddr, va);
                 tmem_ld32_wait(taddr + 32, vb);
-                tmem_ld2_wait(taddr + 128, g0, g1);
-                const float mA = fmaxf(max32(va), max32(vb));
+                rmax[2 * pr] = fmaxf(max32(va), max32(vb));
                 tmem_ld32_wait(taddr + 64, va);
                 tmem_ld32_wait(taddr + 96, vb);
                 tc_fence_before();
-                mbar_arrive(&t_empty[ts]);
-                const float mB = fmaxf(max32(va), max32(vb));
+                mbar_arrive(&t_empty[g]);
+                rmax[2 * pr + 1] = fmaxf(max32(va), max32(vb));
                 if (quad == 0) PTL(9 + g, jn, 2);
-                const float bb = (m == 0) ? b1v[0] : ((m == 1) ? b1v[1] : b1v[2]);
-                const int c = m * 128 + cl;
-                // which of the pair's items hold a pillar: written by the front end before the pair's operands were released
-                const unsigned vv = *reinterpret_cast<const unsigned short*>(sValid + (p & (kValidRing - 1)) * 2);
-                const bool v0 = (vv & 0xFFu) != 0, v1 = (vv >> 8) != 0;
+            }
+            // ---- W1b' hmax of the unit's 8 items (one MMA per unit), bias, relu, the 8 cells ---------------------------
+            float gv[8];
+            mbar_wait(&gt_full[g], (uint32_t)j & 1u);
+            tc_fence_after();
+            tmem_ld8_wait(taddr + 128, gv);
+            tc_fence_before();
+            mbar_arrive(&gt_empty[g]);
+            // which items hold a pillar: written by the front end before the pairs' operands were released
+            const uint2 vv = *reinterpret_cast<const uint2*>(sValid + ((j * kPairsPerUnit) & (kValidRing - 1)) * 2);
+            float ob[kUnit];
+#pragma unroll
+            for (int i = 0; i < kUnit; ++i) {
+                const unsigned word = i < 4 ? vv.x : vv.y;
+                const bool v = ((word >> (8 * (i & 3))) & 0xFFu) != 0;
+                ob[i] = v ? fmaxf(rmax[i] + (gv[i] + bb), 0.f) : 0.f;
+            }
+            if (c < C) {
                 if (fast) {
-                    const float o0 = v0 ? fmaxf(mA + (g0 + bb), 0.f) : 0.f;
-                    const float o1 = v1 ? fmaxf(mB + (g1 + bb), 0.f) : 0.f;
-                    if (c < C) {
-                        if (nchw) {
-                            const int64_t i0 = ((int64_t)ub * a.c_total + a.c_offset + c) * ipt + ur + 2 * pr;
-                            if (f32) *reinterpret_cast<float2*>(static_cast<float*>(a.out) + i0) = make_float2(o0, o1);
-                            else *reinterpret_cast<uint32_t*>(static_cast<unsigned short*>(a.out) + i0) = pack_bf16(o0, o1);
-                        } else if (f32) {
-                            // (B, ny nx, C) rows: a warp writes 32 consecutive channels of each of the pair's two cells
-                            float* dst = static_cast<float*>(a.out) + (int64_t)item * C + c;
-                            dst[0] = o0;
-                            dst[C] = o1;
+                    if (nchw) {
+                        const int64_t i0 = ((int64_t)ub * a.c_total + a.c_offset + c) * ipt + ur;
+                        if (f32) {
+                            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(a.out) + i0);
+                            dst[0] = make_float4(ob[0], ob[1], ob[2], ob[3]);
+                            dst[1] = make_float4(ob[4], ob[5], ob[6], ob[7]);
                         } else {
-                            unsigned short* dst = static_cast<unsigned short*>(a.out) + (int64_t)item * C + c;
-                            dst[0] = (unsigned short)(pack_bf16(o0, 0.f) & 0xFFFF);
-                            dst[C] = (unsigned short)(pack_bf16(o1, 0.f) & 0xFFFF);
+                            *reinterpret_cast<uint4*>(static_cast<unsigned short*>(a.out) + i0) =
+                                make_uint4(pack_bf16(ob[0], ob[1]), pack_bf16(ob[2], ob[3]), pack_bf16(ob[4], ob[5]), pack_bf16(ob[6], ob[7]));
                         }
+                    } else if (f32) {
+                        // (B, ny nx, C) rows: a warp writes 32 consecutive channels of each of the unit's 8 cells
+                        float* dst = static_cast<float*>(a.out) + (int64_t)item0 * C + c;
+#pragma unroll
+                        for (int i = 0; i < kUnit; ++i) dst[(int64_t)i * C] = ob[i];
+                    } else {
+                        unsigned short* dst = static_cast<unsigned short*>(a.out) + (int64_t)item0 * C + c;
+#pragma unroll
+                        for (int i = 0; i < kUnit; ++i) dst[(int64_t)i * C] = (unsigned short)(pack_bf16(ob[i], 0.f) & 0xFFFF);
                     }
                 } else {
-                    int b0 = ub, r0 = ur + 2 * pr, b1, r1;
-                    if (r0 >= ipt) { r0 -= ipt; ++b0; }
-                    b1 = b0; r1 = r0 + 1;
-                    if (r1 >= ipt) { r1 -= ipt; ++b1; }
-                    const float o0 = v0 ? fmaxf(mA + (g0 + bb), 0.f) : 0.f;
-                    const float o1 = v1 ? fmaxf(mB + (g1 + bb), 0.f) : 0.f;
-                    if (c < C) {
-                        if (nchw) {
-                            if (item < total_items) store_scalar(a, ((int64_t)b0 * a.c_total + a.c_offset + c) * ipt + r0, o0);
-                            if (item + 1 < total_items) store_scalar(a, ((int64_t)b1 * a.c_total + a.c_offset + c) * ipt + r1, o1);
-                        } else {
-                            // list rows past num_pillars stay untouched, canvas cells are always written
-                            const int64_t i0 = (int64_t)item * C + c;
-                            if (item < total_items && (v0 || canvas)) store_scalar(a, i0, o0);
-                            if (item + 1 < total_items && (v1 || canvas)) store_scalar(a, i0 + C, o1);
+                    int bi = ub, ri = ur;
+#pragma unroll
+                    for (int i = 0; i < kUnit; ++i) {
+                        const int item = item0 + i;
+                        const unsigned word = i < 4 ? vv.x : vv.y;
+                        const bool v = ((word >> (8 * (i & 3))) & 0xFFu) != 0;
+                        // list rows past num_pillars stay untouched, canvas cells are always written
+                        if (item < total_items && (v || canvas)) {
+                            const int64_t idx = nchw ? ((int64_t)bi * a.c_total + a.c_offset + c) * ipt + ri : (int64_t)item * C + c;
+                            store_scalar(a, idx, ob[i]);
                         }
+                        if (++ri >= ipt) { ri = 0; ++bi; }
                     }
                 }
-                if (quad == 0) PTL(9 + g, jn, 3);
-                ++jn;
             }
+            if (quad == 0) PTL(9 + g, jn - 1, 3);
         }
     }
     tc_fence_before();
