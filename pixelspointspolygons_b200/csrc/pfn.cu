@@ -340,7 +340,7 @@ constexpr int kTcThreads = 32 * (kEpiWarp0 + 4 * kEpiGroups);
 #endif
 #ifndef P3P_REG_MMA
 #define P3P_REG_MMA 40
-#define P3P_REG_FRONT 112
+#define P3P_REG_FRONT 104
 #define P3P_REG_EPI 72
 #endif
 constexpr int kRegMma = P3P_REG_MMA, kRegFront = P3P_REG_FRONT, kRegEpi = P3P_REG_EPI;  // registers per thread after setmaxnreg (launch: 80)
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     // (MMA / front / epilogue -> fp16, tf32 kernel time), per-pair W1b'hmax MMA: 40/112/72 -> 43.3, 68.9 us; 40/120/64 ->
     // 43.9, 52.4 us; 40/136/56 -> 44.6, 53.1 us; 24/104/80 -> 78.6, 55.2 us (the issuers spill below 32); no reallocation
     // -> 47.1, 56.4 us.  With the per-unit W1b'hmax MMA (the epilogue holds a unit's 8 maxima): 40/120/64 -> 45.0, 52.2 us;
-    // 40/112/72 -> 39.6, 50.9 us.
+    // 40/112/72 -> 39.6, 50.9 us; 40/104/72 -> 38.6, 49.0 us; 40/96/80 -> 66.9, 85.7 us (the front end spills below 104).
     if (warp < kMmaWarps) {
         setmaxnreg_dec<kRegMma>();
         // =========================== MMA issuers: warp m owns channel tile m and accumulator stage m ===========================
