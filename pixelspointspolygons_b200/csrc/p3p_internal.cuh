@@ -307,29 +307,14 @@ __device__ __forceinline__ uint32_t make_idesc(int fmt_code, int m, int n) {
     const uint32_t fmt = (uint32_t)fmt_code;  // F16F32Format: F16 = 0, BF16 = 1, TF32 = 2
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-// tcgen05.ld + tcgen05.wait::ld in ONE asm statement: the destination registers are only defined once the
-// wait has retired, so no consumer can be scheduled between the load and the wait.
-__device__ __forceinline__ void tmem_ld64_wait(uint32_t taddr, float (&v)[64]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];\n"
-        "tcgen05.wait::ld.sync.aligned;\n"
-        : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15]),"=f"(v[16]),"=f"(v[17]),"=f"(v[18]),"=f"(v[19]),"=f"(v[20]),"=f"(v[21]),"=f"(v[22]),"=f"(v[23]),"=f"(v[24]),"=f"(v[25]),"=f"(v[26]),"=f"(v[27]),"=f"(v[28]),"=f"(v[29]),"=f"(v[30]),"=f"(v[31]),"=f"(v[32]),"=f"(v[33]),"=f"(v[34]),"=f"(v[35]),"=f"(v[36]),"=f"(v[37]),"=f"(v[38]),"=f"(v[39]),"=f"(v[40]),"=f"(v[41]),"=f"(v[42]),"=f"(v[43]),"=f"(v[44]),"=f"(v[45]),"=f"(v[46]),"=f"(v[47]),"=f"(v[48]),"=f"(v[49]),"=f"(v[50]),"=f"(v[51]),"=f"(v[52]),"=f"(v[53]),"=f"(v[54]),"=f"(v[55]),"=f"(v[56]),"=f"(v[57]),"=f"(v[58]),"=f"(v[59]),"=f"(v[60]),"=f"(v[61]),"=f"(v[62]),"=f"(v[63])
-        : "r"(taddr)
-        : "memory");
-}
+// tcgen05.ld + tcgen05.wait::ld in ONE asm statement: the destination registers are only defined once the wait has
+// retired, so no consumer can be scheduled between the load and the wait.  (ptxas tracks the load's registers with a
+// scoreboard, so loads into distinct registers still overlap with the arithmetic on earlier ones.)
 __device__ __forceinline__ void tmem_ld32_wait(uint32_t taddr, float (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
         "tcgen05.wait::ld.sync.aligned;\n"
         : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15]),"=f"(v[16]),"=f"(v[17]),"=f"(v[18]),"=f"(v[19]),"=f"(v[20]),"=f"(v[21]),"=f"(v[22]),"=f"(v[23]),"=f"(v[24]),"=f"(v[25]),"=f"(v[26]),"=f"(v[27]),"=f"(v[28]),"=f"(v[29]),"=f"(v[30]),"=f"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld2_wait(uint32_t taddr, float& a, float& b) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n"
-        "tcgen05.wait::ld.sync.aligned;\n"
-        : "=f"(a), "=f"(b)
         : "r"(taddr)
         : "memory");
 }
@@ -372,11 +357,6 @@ __device__ __forceinline__ void fix_split(float v, float scale, int& lo, int& hi
 }
 __device__ __forceinline__ float fix_mean(int sum_lo, int sum_hi, float inv_scale, float n) {
     return __fdiv_rn(__fmaf_rn((float)sum_hi, 65536.0f, (float)sum_lo) * inv_scale, n);
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
 }
 
 #endif  // __CUDACC__
