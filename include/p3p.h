@@ -161,6 +161,20 @@ int p3p_encode(const float* points, int32_t point_stride, const int64_t* tile_of
                int32_t lidar_zero, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The LiDAR-only ViT input: the fused hot path emitting the token sequence the transformer blocks
+ * consume, i.e. what timm's `VisionTransformer._pos_embed(self.patch_embed(x))` returns in eval mode for the reference's
+ * `vit_small_patch8_224` (one class token, no register tokens, `no_embed_class = False`; call site
+ * pixelspointspolygons/models/pointpillars/pointpillars_vit.py:64,74):
+ *   tokens[b, 0, :]        = cls_token + pos_embed[0, :]
+ *   tokens[b, 1 + cell, :] = encoder(b, cell, :) + pos_embed[1 + cell, :]      (empty cells: pos_embed only)
+ * tokens: (B, 1 + ny*nx, C) fp32; cls_token: (C) fp32; pos_embed: (1 + ny*nx, C) fp32, all on the device.
+ */
+int p3p_encode_tokens(const float* points, int32_t point_stride, const int64_t* tile_offsets, int32_t num_tiles,
+                      int64_t total_points, const p3p_grid* grid, const void* blob, int32_t channels, int32_t precision,
+                      const float* cls_token, const float* pos_embed, float* tokens, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/*
  * Image patch embedding: Conv2d(in_chans, C, kernel=P, stride=P, bias) on (B, in_chans, H, W) fp32,
  * written NCHW into channels [c_offset, c_offset + C) of out (B, c_total, H/P, W/P).
  * weight: (C, in_chans, P, P) fp32; bias: (C) fp32 or NULL.

@@ -386,3 +386,14 @@ def synth_weights(seed: int, feat_channels=(64, 384), in_channels=3, patch=8, im
     sd_img = {"proj.weight": torch.randn(C, img_chans, patch, patch, generator=g) / (k ** 0.5),
               "proj.bias": torch.randn(C, generator=g) * 0.1}
     return sd, sd_img
+
+
+def vit_tokens(x_tokens: torch.Tensor, cls_token: torch.Tensor, pos_embed: torch.Tensor) -> torch.Tensor:
+    """timm `VisionTransformer._pos_embed` in eval mode for the reference's `vit_small_patch8_224.dino` (one class
+    token, no register tokens, `no_embed_class = False`, `pos_drop` = identity; the caller is
+    R:pixelspointspolygons/models/pointpillars/pointpillars_vit.py:74 `self.vit.forward_features(x_lidar)`):
+    x = cat([cls_token.expand(B, -1, -1), x], dim=1) + pos_embed.   x_tokens: (B, L, C) -> (B, 1 + L, C)."""
+    B = x_tokens.shape[0]
+    x = torch.cat([cls_token.reshape(1, 1, -1).expand(B, -1, -1).to(x_tokens.dtype), x_tokens], dim=1)
+    return x + pos_embed.reshape(1, x.shape[1], -1).to(x_tokens.dtype)
+

@@ -307,6 +307,42 @@ int p3p_encode(const float* points, int32_t point_stride, const int64_t* tile_of
     return rc;
 }
 
+int p3p_encode_tokens(const float* points, int32_t point_stride, const int64_t* tile_offsets, int32_t num_tiles,
+                      int64_t total_points, const p3p_grid* grid, const void* blob, int32_t channels, int32_t precision,
+                      const float* cls_token, const float* pos_embed, float* tokens, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    GridDev g;
+    WsLayout l;
+    WsPtrs ws;
+    BlobLayout bl;
+    int rc = common_setup(points, point_stride, tile_offsets, num_tiles, total_points, grid, workspace, workspace_bytes, &g, &l, &ws);
+    if (rc) return rc;
+    rc = check_blob(channels, &bl);
+    if (rc) return rc;
+    if (!tokens || !aligned16(tokens)) return fail(P3P_ERR_INVALID_ARGUMENT, "tokens null or misaligned");
+    if (!blob || !aligned16(blob)) return fail(P3P_ERR_INVALID_ARGUMENT, "blob null or misaligned");
+    if (!cls_token || !pos_embed) return fail(P3P_ERR_INVALID_ARGUMENT, "cls_token or pos_embed is null");
+    if (num_tiles == 0) return P3P_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PfnArgs a;
+    fill_pfn_args(&a, g, ws, blob, bl, num_tiles);
+    a.item_mode = kItemsCanvas;
+    a.items_per_tile = g.ny * g.nx;
+    a.num_items = (int64_t)num_tiles * a.items_per_tile;
+    a.out = tokens;
+    a.out_layout = P3P_LAYOUT_NLC;
+    a.out_dtype = P3P_DTYPE_F32;
+    a.c_total = 0;
+    a.c_offset = 0;
+    a.pos_embed = pos_embed;
+    a.token_rows = a.items_per_tile + 1;
+    rc = launch_cls_rows(a, cls_token, st);
+    if (rc) return rc;
+    rc = launch_voxelize(points, point_stride, tile_offsets, num_tiles, total_points, g, l, ws, nullptr, 0, st);
+    if (rc) return rc;
+    return run_pfn(a, precision, st);
+}
+
 int p3p_profile_begin(int32_t max_records) {
     if (max_records < 1 || max_records > 100000) return fail(P3P_ERR_INVALID_ARGUMENT, "max_records %d", max_records);
     for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);

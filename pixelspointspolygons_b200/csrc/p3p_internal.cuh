@@ -145,6 +145,10 @@ struct PfnArgs {
     int out_layout;  // P3P_LAYOUT_*
     int out_dtype;   // P3P_DTYPE_*
     int c_total, c_offset;
+    // token sequence output (p3p_encode_tokens): rows of C channels, 1 + items_per_tile rows per tile, row 0 = class
+    // token; pos_embed (1 + items_per_tile, C) is added to every row.  token_rows == 0: off
+    const float* pos_embed;
+    int token_rows;
 };
 
 // launchers (host) ---------------------------------------------------------------------------------
@@ -155,6 +159,7 @@ int launch_pfn_prepare(const p3p_pfn_params* p, int precision, char* blob, const
 int launch_pfn_simt(const PfnArgs& a, cudaStream_t st);
 int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st);
 int launch_zero_lidar(const PfnArgs& a, cudaStream_t st);
+int launch_cls_rows(const PfnArgs& a, const float* cls_token, cudaStream_t st);
 int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, int P, const float* weight,
                        const float* bias, int C, int precision, void* out, int out_dtype, int c_total, int c_offset,
                        cudaStream_t st);

@@ -152,6 +152,14 @@ __device__ __forceinline__ int64_t out_index(const PfnArgs& a, int64_t item, int
         return ((int64_t)b * a.c_total + a.c_offset + c) * a.items_per_tile + cell;
     return item * a.bl.C + c;
 }
+// one output value of item (b, cell): plain layouts, or the token sequence (row 1 + cell of the tile, + pos_embed)
+__device__ __forceinline__ void store_item(const PfnArgs& a, int64_t item, int b, int cell, int c, float v) {
+    if (a.token_rows) {
+        static_cast<float*>(a.out)[((int64_t)b * a.token_rows + 1 + cell) * a.bl.C + c] = v + a.pos_embed[(int64_t)(1 + cell) * a.bl.C + c];
+        return;
+    }
+    store_scalar(a, out_index(a, item, b, cell, c), v);
+}
 
 // ------------------------------------------------------------------------------------------------
 // exact fp32 kernel (literal formulation)
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(kSimtMaxThreads) pfn_simt_kernel(PfnArgs a) {
         const Item it = fetch_item(a, item);
         if (!it.valid) {
             if (a.item_mode == kItemsCanvas)
-                for (int c = tid; c < C; c += nthreads) store_scalar(a, out_index(a, item, it.b, it.cell, c), 0.f);
+                for (int c = tid; c < C; c += nthreads) store_item(a, item, it.b, it.cell, c, 0.f);
             continue;
         }
         const float4* slot = item_slots(a, it);
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(kSimtMaxThreads) pfn_simt_kernel(PfnArgs a) {
                     }
                     best = fmaxf(best, acc);
                 }
-                store_scalar(a, out_index(a, item, it.b, it.cell, tid), fmaxf(best + g, 0.f));
+                store_item(a, item, it.b, it.cell, tid, fmaxf(best + g, 0.f));
             }
         } else {
             for (int c = tid; c < C; c += nthreads) {
@@ -305,10 +313,21 @@ __global__ void __launch_bounds__(kSimtMaxThreads) pfn_simt_kernel(PfnArgs a) {
                     }
                     best = fmaxf(best, acc);
                 }
-                store_scalar(a, out_index(a, item, it.b, it.cell, c), fmaxf(best + g, 0.f));
+                store_item(a, item, it.b, it.cell, c, fmaxf(best + g, 0.f));
             }
         }
         __syncthreads();
+    }
+}
+
+// class-token rows of the token sequence: tokens[b, 0, :] = cls_token + pos_embed[0, :]
+__global__ void cls_rows_kernel(PfnArgs a, const float* __restrict__ cls_token) {
+    const int C = a.bl.C;
+    const int64_t total = (int64_t)a.B * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / C;
+        const int c = (int)(i - b * C);
+        static_cast<float*>(a.out)[b * a.token_rows * C + c] = cls_token[c] + a.pos_embed[c];
     }
 }
 
@@ -825,7 +844,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         const bool f32 = (kMode != 0) || (a.out_dtype == P3P_DTYPE_F32);
         const int C = a.bl.C, ipt = a.items_per_tile;
         // fast path: whole units inside one tile, every item exists -> no per-item bounds, two-cell vector stores
-        const bool fast = (kMode != 0) || (canvas && (total_items % kUnit == 0) && (ipt % kUnit == 0));
+        const bool fast = (kMode != 0) || (canvas && (total_items % kUnit == 0) && (ipt % kUnit == 0) && a.token_rows == 0);
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int cl = quad * 32 + lane;  // channel inside a 128-channel tile
         float b1v[3];
@@ -911,8 +930,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                         const bool v = ((word >> (8 * (i & 3))) & 0xFFu) != 0;
                         // list rows past num_pillars stay untouched, canvas cells are always written
                         if (item < total_items && (v || canvas)) {
-                            const int64_t idx = nchw ? ((int64_t)bi * a.c_total + a.c_offset + c) * ipt + ri : (int64_t)item * C + c;
-                            store_scalar(a, idx, ob[i]);
+                            if (a.token_rows) {  // token sequence: row 1 + cell of the tile, + pos_embed
+                                static_cast<float*>(a.out)[((int64_t)bi * a.token_rows + 1 + ri) * C + c] =
+                                    ob[i] + a.pos_embed[(int64_t)(1 + ri) * C + c];
+                            } else {
+                                const int64_t idx = nchw ? ((int64_t)bi * a.c_total + a.c_offset + c) * ipt + ri : (int64_t)item * C + c;
+                                store_scalar(a, idx, ob[i]);
+                            }
                         }
                         if (++ri >= ipt) { ri = 0; ++bi; }
                     }
@@ -957,6 +981,14 @@ int launch_pfn_simt(const PfnArgs& a, cudaStream_t st) {
     return P3P_OK;
 }
 
+int launch_cls_rows(const PfnArgs& a, const float* cls_token, cudaStream_t st) {
+    if (a.B <= 0) return P3P_OK;
+    const int64_t total = (int64_t)a.B * a.bl.C;
+    cls_rows_kernel<<<(unsigned)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024), 256, 0, st>>>(a, cls_token);
+    P3P_CUDA_CHECK(cudaGetLastError());
+    return P3P_OK;
+}
+
 int launch_zero_lidar(const PfnArgs& a, cudaStream_t st) {
     if (a.num_items <= 0) return P3P_OK;
     zero_lidar_kernel<<<device_sm_count() * 4, 256, 0, st>>>(a);
@@ -982,7 +1014,8 @@ int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st) {
     int64_t grid = device_sm_count();
     if (grid > units) grid = units;
     int mode = 0;
-    if (a.item_mode == kItemsCanvas && a.num_items % kUnit == 0 && a.items_per_tile % kUnit == 0 && a.out_dtype == P3P_DTYPE_F32)
+    if (a.item_mode == kItemsCanvas && a.num_items % kUnit == 0 && a.items_per_tile % kUnit == 0 && a.out_dtype == P3P_DTYPE_F32 &&
+        a.token_rows == 0)
         mode = (a.out_layout == P3P_LAYOUT_NCHW) ? 2 : 1;
     // Programmatic dependent launch: the CTAs start (TMEM allocation, barriers, weights -> shared memory) while the
     // voxelizer's last chunks drain, and wait for its results with griddepcontrol.wait before their first read.

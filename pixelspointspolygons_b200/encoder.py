@@ -242,6 +242,33 @@ class PointPillarsEncoder(nn.Module):
         _lib.check(rc, "p3p_encode")
         return out
 
+    @torch.no_grad()
+    def forward_tokens(self, x_lidar, cls_token: torch.Tensor, pos_embed: torch.Tensor,
+                       precision: Optional[str] = None) -> torch.Tensor:
+        """The ViT input of the LiDAR-only encoders in one call: what timm's
+        `vit._pos_embed(vit.patch_embed(x_lidar))` returns in eval mode with this module as `vit.patch_embed`
+        (R:pixelspointspolygons/models/pointpillars/pointpillars_vit.py:64,74; one class token, no register tokens,
+        `no_embed_class = False`): (B, 1 + ny*nx, C) fp32, row 0 = cls_token + pos_embed[0], row 1 + cell =
+        encoder output + pos_embed[1 + cell].  cls_token: (1, 1, C); pos_embed: (1, 1 + ny*nx, C)."""
+        values, offsets, B = self._pack(x_lidar)
+        device, hw, Cc = values.device, self.ny * self.nx, self.channels
+        if cls_token.numel() != Cc or pos_embed.numel() != (hw + 1) * Cc:
+            raise ValueError(f"cls_token must hold {Cc} and pos_embed {(hw + 1) * Cc} values")
+        cls = cls_token.detach().to(device=device, dtype=torch.float32).contiguous()
+        pos = pos_embed.detach().to(device=device, dtype=torch.float32).contiguous()
+        precision = self._resolve_precision(precision)
+        grid, total = self._grid(), values.shape[0]
+        out = torch.empty(B, hw + 1, Cc, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            ws = self._workspace(grid, B, total, device)
+            blob = self._blob(device, precision)
+            rc = _lib.lib().p3p_encode_tokens(values.data_ptr(), values.shape[1], offsets.data_ptr(), B, total, C.byref(grid),
+                                              blob.data_ptr(), Cc, P3P_PRECISION[precision], cls.data_ptr(), pos.data_ptr(),
+                                              out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "p3p_encode_tokens")
+        return out
+
     def forward(self, x_lidar, return_flattened: bool = True):
         if self.training:
             return self._forward_dense(x_lidar, return_flattened)

@@ -229,6 +229,24 @@ def test_full_size_batch_properties(cuda_device):
     assert raw["num_pillars"].max() <= 784
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "fp16"])
+def test_vit_token_sequence_matches_oracle(cuda_device, prec):
+    """class token + positional embedding fused into the encoder's store (p3p_encode_tokens)."""
+    grid = po.GridSpec()
+    enc, ref = build(cuda_device, grid, seed=13)
+    g = torch.Generator().manual_seed(5)
+    cls = torch.randn(1, 1, 384, generator=g) * 0.5
+    pos = torch.randn(1, 785, 384, generator=g) * 0.2
+    tiles = [po.synth_tile(7000, 41), np.zeros((0, 3), np.float32), po.synth_tile(30000, 42, clustered=True)]
+    with torch.no_grad():
+        r = po.vit_tokens(ref(tiles), cls, pos)
+        a = enc.forward_tokens(to_nested(tiles, cuda_device), cls.to(cuda_device), pos.to(cuda_device), precision=prec)
+    assert a.shape == (3, 785, 384)
+    assert torch.equal(a[:, 0].cpu(), (cls + pos[:, :1]).reshape(1, 384).expand(3, -1))  # class-token rows: exact
+    assert torch.equal(a[1, 1:].cpu(), pos[0, 1:])  # the empty tile: positional embedding only
+    assert_close(a, r, TOL[prec], f"tokens {prec}")
+
+
 def test_multi_wave_batch_with_dependent_launch(cuda_device):
     """40 tiles x 60k points = about 1000 ranking chunks, more than two waves of the voxelizer grid: the PFN grid is a
     programmatic dependent launch that may start while the voxelizer's last wave drains -- no deadlock, same results."""

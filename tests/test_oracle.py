@@ -167,3 +167,16 @@ def test_early_fusion_concat_order():
     assert x.shape == (1, 768, 28, 28)
     assert torch.equal(x[:, :384], pe(img)) and torch.equal(x[:, 384:], enc(tiles, return_flattened=False))
     assert z[:, 384:].abs().sum() == 0 and torch.equal(z[:, :384], x[:, :384])
+
+
+def test_vit_tokens_is_cat_cls_plus_pos():
+    import torch
+
+    x = torch.arange(2 * 3 * 4, dtype=torch.float32).reshape(2, 3, 4)
+    cls = torch.full((1, 1, 4), 100.0)
+    pos = torch.arange(4 * 4, dtype=torch.float32).reshape(1, 4, 4) * 0.5
+    t = po.vit_tokens(x, cls, pos)
+    assert t.shape == (2, 4, 4)
+    assert torch.equal(t[:, 0], (cls[0, 0] + pos[0, 0]).expand(2, -1))
+    assert torch.equal(t[1, 2], x[1, 1] + pos[0, 2])
+
