@@ -464,8 +464,9 @@ __device__ __forceinline__ float max32(const float (&v)[32]) {
 //   3 x 4 epilogue warps: group g reads accumulator stage g: tcgen05.ld, max over each
 //                        pillar's 64 columns with 3-input max, + W1b' hmax + b1, relu, store of the two cells.
 // kMode: 0 = any item source / layout / dtype (run-time branches); 1 = canvas items, whole units inside one tile, fp32 rows
-// of C channels (B, ny nx, C); 2 = the same into the fp32 NCHW (concat) buffer.  Modes 1 and 2 are the shipped encoder
-// configurations with every run-time branch of the steady-state loops resolved at compile time.
+// of C channels (B, ny nx, C); 2 = the same into the fp32 NCHW (concat) buffer; 3 = the same as token rows 1 + cell of a
+// (B, 1 + ny nx, C) sequence with pos_embed added.  Modes 1-3 are the shipped encoder configurations with every run-time
+// branch of the steady-state loops resolved at compile time.
 template <int kPrec, int kMode>
 __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     using Cfg = TcCfg<kPrec>;
@@ -845,6 +846,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         const int C = a.bl.C, ipt = a.items_per_tile;
         // fast path: whole units inside one tile, every item exists -> no per-item bounds, two-cell vector stores
         const bool fast = (kMode != 0) || (canvas && (total_items % kUnit == 0) && (ipt % kUnit == 0) && a.token_rows == 0);
+        const bool tokens = (kMode == 3);
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int cl = quad * 32 + lane;  // channel inside a 128-channel tile
         float b1v[3];
@@ -900,7 +902,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                 ob[i] = v ? fmaxf(rmax[i] + (gv[i] + bb), 0.f) : 0.f;
             }
             if (c < C) {
-                if (fast) {
+                if (tokens) {
+                    // token sequence: rows 1 + cell of the tile, positional embedding added on the way out
+                    const int64_t row = (int64_t)ub * a.token_rows + 1 + ur;
+                    float* dst = static_cast<float*>(a.out) + row * C + c;
+                    const float* pe = a.pos_embed + (int64_t)(1 + ur) * C + c;
+#pragma unroll
+                    for (int i = 0; i < kUnit; ++i) dst[(int64_t)i * C] = ob[i] + __ldg(pe + (int64_t)i * C);
+                } else if (fast) {
                     if (nchw) {
                         const int64_t i0 = ((int64_t)ub * a.c_total + a.c_offset + c) * ipt + ur;
                         if (f32) {
@@ -1004,9 +1013,9 @@ int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st) {
 #define P3P_TC_ATTR(PREC, MODE)                                                                                         \
     P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<PREC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         (int)TcCfg<PREC>::kSmemBytes))
-        P3P_TC_ATTR(P3P_PRECISION_TF32, 0); P3P_TC_ATTR(P3P_PRECISION_TF32, 1); P3P_TC_ATTR(P3P_PRECISION_TF32, 2);
-        P3P_TC_ATTR(P3P_PRECISION_BF16, 0); P3P_TC_ATTR(P3P_PRECISION_BF16, 1); P3P_TC_ATTR(P3P_PRECISION_BF16, 2);
-        P3P_TC_ATTR(P3P_PRECISION_FP16, 0); P3P_TC_ATTR(P3P_PRECISION_FP16, 1); P3P_TC_ATTR(P3P_PRECISION_FP16, 2);
+        P3P_TC_ATTR(P3P_PRECISION_TF32, 0); P3P_TC_ATTR(P3P_PRECISION_TF32, 1); P3P_TC_ATTR(P3P_PRECISION_TF32, 2); P3P_TC_ATTR(P3P_PRECISION_TF32, 3);
+        P3P_TC_ATTR(P3P_PRECISION_BF16, 0); P3P_TC_ATTR(P3P_PRECISION_BF16, 1); P3P_TC_ATTR(P3P_PRECISION_BF16, 2); P3P_TC_ATTR(P3P_PRECISION_BF16, 3);
+        P3P_TC_ATTR(P3P_PRECISION_FP16, 0); P3P_TC_ATTR(P3P_PRECISION_FP16, 1); P3P_TC_ATTR(P3P_PRECISION_FP16, 2); P3P_TC_ATTR(P3P_PRECISION_FP16, 3);
 #undef P3P_TC_ATTR
         attr_done = true;
     }
@@ -1014,9 +1023,8 @@ int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st) {
     int64_t grid = device_sm_count();
     if (grid > units) grid = units;
     int mode = 0;
-    if (a.item_mode == kItemsCanvas && a.num_items % kUnit == 0 && a.items_per_tile % kUnit == 0 && a.out_dtype == P3P_DTYPE_F32 &&
-        a.token_rows == 0)
-        mode = (a.out_layout == P3P_LAYOUT_NCHW) ? 2 : 1;
+    if (a.item_mode == kItemsCanvas && a.num_items % kUnit == 0 && a.items_per_tile % kUnit == 0 && a.out_dtype == P3P_DTYPE_F32)
+        mode = a.token_rows ? 3 : ((a.out_layout == P3P_LAYOUT_NCHW) ? 2 : 1);
     // Programmatic dependent launch: the CTAs start (TMEM allocation, barriers, weights -> shared memory) while the
     // voxelizer's last chunks drain, and wait for its results with griddepcontrol.wait before their first read.
     cudaLaunchAttribute attr[1];
@@ -1037,6 +1045,7 @@ int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st) {
     do {                                                  \
         if (mode == 1) P3P_LAUNCH_TC(PREC, 1);            \
         else if (mode == 2) P3P_LAUNCH_TC(PREC, 2);       \
+        else if (mode == 3) P3P_LAUNCH_TC(PREC, 3);       \
         else P3P_LAUNCH_TC(PREC, 0);                      \
     } while (0)
     if (precision == P3P_PRECISION_TF32) P3P_LAUNCH_TC_MODES(P3P_PRECISION_TF32);
