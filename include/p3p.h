@@ -119,6 +119,17 @@ typedef struct p3p_voxel_outputs {
     int32_t* cell_owner;       /* (B, ny*nx) voxel ordinal that owns each canvas cell (last writer), -1 if empty */
 } p3p_voxel_outputs;
 
+/* Per-tile constants of p3p_las_to_pixels (a device array of num_tiles entries). */
+typedef struct p3p_las_tile {
+    double scale[3];         /* las.header.scales */
+    double offset[3];        /* las.header.offsets */
+    double left, top;        /* img_info['top_left'] (ignored when origin_from_min) */
+    double res;              /* img_info.get('res_x', 0.25) */
+    double height, width;    /* img_info['height'], img_info['width'] (pixels) */
+    int32_t origin_from_min; /* 1: the tile's own x / y minimum is the origin (predictor.py:126) */
+    int32_t clip;            /* 1: clip x to [0, width], y to [0, height] (p3_coco.py:95-96) */
+} p3p_las_tile;
+
 const char* p3p_last_error(void);
 int p3p_version(void);
 
@@ -182,6 +193,18 @@ int p3p_encode_tokens(const float* points, int32_t point_stride, const int64_t* 
 int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, int32_t height, int32_t width,
                     int32_t patch, const float* weight, const float* bias, int32_t channels, int32_t precision,
                     void* out, int32_t out_dtype, int32_t c_total, int32_t c_offset, void* stream);
+
+/*
+ * LiDAR input front end: raw LAS integer coordinates of a jagged batch -> the (total_points, 3)
+ * fp32 pixel-space points p3p_encode consumes, bit-identical to the numpy / scikit-learn code of
+ * P3Dataset.load_lidar_points (p3_coco.py:74-101; clip = 1) and Predictor.load_lidar_from_file (predictor.py:116-137;
+ * origin_from_min = 1, clip = 0): x = (X*sx+ox - left)/res, y = height - (Y*sy+oy - top)/res, z = MinMaxScaler over the
+ * tile to [0, z_hi], all in float64, then float32.  X, Y, Z: (total_points) int32; tile_offsets: (B + 1) int64;
+ * minmax_ws: 4 * num_tiles int32 of scratch.  Everything on the device.
+ */
+int p3p_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, const int64_t* tile_offsets, int32_t num_tiles,
+                      int64_t total_points, const p3p_las_tile* tiles, double z_hi, int32_t* minmax_ws, float* points,
+                      void* stream);
 
 /*
  * Measurement hooks (bench.py's roofline leg; no reference counterpart).  Between begin and end every

@@ -397,3 +397,36 @@ def vit_tokens(x_tokens: torch.Tensor, cls_token: torch.Tensor, pos_embed: torch
     x = torch.cat([cls_token.reshape(1, 1, -1).expand(B, -1, -1).to(x_tokens.dtype), x_tokens], dim=1)
     return x + pos_embed.reshape(1, x.shape[1], -1).to(x_tokens.dtype)
 
+
+def las_points_to_pixels(X, Y, Z, scales, offsets, top_left=None, height=224, width=224, res=0.25, z_hi=100.0,
+                         variant="dataset") -> np.ndarray:
+    """Restatement of the reference's LiDAR loaders on raw LAS integers (test infrastructure; numpy float64 exactly as
+    the reference computes): `variant="dataset"` = P3Dataset.load_lidar_points (R:.../datasets/p3_coco.py:74-101),
+    `variant="predict"` = Predictor.load_lidar_from_file (R:.../predict/predictor.py:116-137).  laspy's `las.x` is
+    `las.X * scale + offset` in float64; sklearn's MinMaxScaler(feature_range=(0, z_hi)).fit_transform is
+    `z * scale_ + min_` with `scale_ = (z_hi - 0) / handle_zeros(zmax - zmin)`, `min_ = 0 - zmin * scale_`
+    (scikit-learn, `_handle_zeros_in_scale`: ranges below 10 eps become 1)."""
+    pts = np.vstack((np.asarray(X, np.int32) * np.float64(scales[0]) + np.float64(offsets[0]),
+                     np.asarray(Y, np.int32) * np.float64(scales[1]) + np.float64(offsets[1]),
+                     np.asarray(Z, np.int32) * np.float64(scales[2]) + np.float64(offsets[2]))).transpose()
+    if variant == "dataset":
+        pts[:, :2] = (pts[:, :2] - np.asarray(top_left, np.float64)) / res
+    else:
+        pts[:, :2] = (pts[:, :2] - np.min(pts, axis=0)[:2]) / res
+    pts[:, 1] = height - pts[:, 1]
+    z = pts[:, -1]
+    zmin, zmax = np.nanmin(z), np.nanmax(z)
+    rng = zmax - zmin
+    if rng < 10 * np.finfo(np.float64).eps:
+        rng = 1.0
+    scale_ = (z_hi - 0) / rng
+    min_ = 0 - zmin * scale_
+    z = z * scale_
+    z = z + min_
+    pts[:, -1] = z
+    pts = pts.astype(np.float32)
+    if variant == "dataset":
+        pts[:, 0] = np.clip(pts[:, 0], 0, width)
+        pts[:, 1] = np.clip(pts[:, 1], 0, height)
+    return pts
+

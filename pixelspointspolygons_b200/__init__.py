@@ -5,5 +5,6 @@ Host side mirrors the reference's encoder plugin interface; the compute is libp3
 from .config import AttrDict, default_cfg  # noqa: F401
 from .encoder import PointPillarsEncoder  # noqa: F401
 from .fusion import EarlyFusionFrontEnd, PatchEmbed  # noqa: F401
+from .las import las_to_pixels  # noqa: F401
 
-__all__ = ["AttrDict", "default_cfg", "PointPillarsEncoder", "EarlyFusionFrontEnd", "PatchEmbed"]
+__all__ = ["AttrDict", "default_cfg", "PointPillarsEncoder", "EarlyFusionFrontEnd", "PatchEmbed", "las_to_pixels"]

@@ -14,9 +14,15 @@ P3P_GRID_DROP_OVERFLOW = 1
 
 EXPORTED = [
     "p3p_last_error", "p3p_version", "p3p_workspace_bytes", "p3p_pfn_blob_bytes", "p3p_pfn_prepare",
-    "p3p_voxelize", "p3p_pillar_features", "p3p_encode", "p3p_encode_tokens", "p3p_patch_embed", "p3p_profile_begin",
-    "p3p_profile_end",
+    "p3p_voxelize", "p3p_pillar_features", "p3p_encode", "p3p_encode_tokens", "p3p_patch_embed", "p3p_las_to_pixels",
+    "p3p_profile_begin", "p3p_profile_end",
 ]
+
+
+class LasTile(C.Structure):
+    _fields_ = [("scale", C.c_double * 3), ("offset", C.c_double * 3), ("left", C.c_double), ("top", C.c_double),
+                ("res", C.c_double), ("height", C.c_double), ("width", C.c_double), ("origin_from_min", C.c_int32),
+                ("clip", C.c_int32)]
 
 
 class Grid(C.Structure):
@@ -74,6 +80,8 @@ def lib():
     l.p3p_encode.argtypes = [vp, i32, vp, i32, i64, C.POINTER(Grid), vp, i32, i32, vp, i32, i32, i32, i32, i32, vp, sz, vp]
     l.p3p_encode_tokens.restype = C.c_int
     l.p3p_encode_tokens.argtypes = [vp, i32, vp, i32, i64, C.POINTER(Grid), vp, i32, i32, vp, vp, vp, vp, sz, vp]
+    l.p3p_las_to_pixels.restype = C.c_int
+    l.p3p_las_to_pixels.argtypes = [vp, vp, vp, vp, i32, i64, vp, C.c_double, vp, vp, vp]
     l.p3p_patch_embed.restype = C.c_int
     l.p3p_patch_embed.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp]
     l.p3p_profile_begin.restype = C.c_int

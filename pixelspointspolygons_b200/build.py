@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libp3p.so")
-SOURCES = ["capi.cu", "voxelize.cu", "pfn.cu", "patch_embed.cu"]
+SOURCES = ["capi.cu", "voxelize.cu", "pfn.cu", "patch_embed.cu", "las.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--cudart", "static",

@@ -343,6 +343,17 @@ int p3p_encode_tokens(const float* points, int32_t point_stride, const int64_t* 
     return run_pfn(a, precision, st);
 }
 
+int p3p_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, const int64_t* tile_offsets, int32_t num_tiles,
+                      int64_t total_points, const p3p_las_tile* tiles, double z_hi, int32_t* minmax_ws, float* points,
+                      void* stream) {
+    if (num_tiles < 0 || total_points < 0) return fail(P3P_ERR_INVALID_ARGUMENT, "negative batch or point count");
+    if (num_tiles == 0 || total_points == 0) return P3P_OK;
+    if (!X || !Y || !Z || !tile_offsets || !tiles || !minmax_ws || !points) return fail(P3P_ERR_INVALID_ARGUMENT, "null pointer");
+    if (!(z_hi > 0.0)) return fail(P3P_ERR_INVALID_ARGUMENT, "z_hi %g", z_hi);
+    return launch_las_to_pixels(X, Y, Z, tile_offsets, num_tiles, total_points, tiles, z_hi, minmax_ws, points,
+                                static_cast<cudaStream_t>(stream));
+}
+
 int p3p_profile_begin(int32_t max_records) {
     if (max_records < 1 || max_records > 100000) return fail(P3P_ERR_INVALID_ARGUMENT, "max_records %d", max_records);
     for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);

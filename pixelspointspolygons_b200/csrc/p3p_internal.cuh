@@ -163,6 +163,8 @@ int launch_cls_rows(const PfnArgs& a, const float* cls_token, cudaStream_t st);
 int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, int P, const float* weight,
                        const float* bias, int C, int precision, void* out, int out_dtype, int c_total, int c_offset,
                        cudaStream_t st);
+int launch_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, const int64_t* offsets, int B, int64_t total,
+                         const p3p_las_tile* tiles, double z_hi, int32_t* mm, float* out, cudaStream_t st);
 int device_sm_count();
 
 // ----------------------------------------------------------------------------------------------

@@ -1,0 +1,57 @@
+"""LiDAR input front end: raw LAS integer coordinates -> pixel-space (N, 3) fp32 points, on the GPU.
+
+Mirrors the numpy / scikit-learn body of `P3Dataset.load_lidar_points`
+(R:pixelspointspolygons/datasets/p3_coco.py:74-101, `variant="dataset"`) and `Predictor.load_lidar_from_file`
+(R:pixelspointspolygons/predict/predictor.py:116-137, `variant="predict"`), bit for bit, for a whole jagged batch:
+the loader hands over `las.X / las.Y / las.Z` (int32) and the header's scales / offsets instead of `las.x / y / z`,
+and gets the `values` tensor of the jagged batch `PointPillarsEncoder` consumes (same offsets).  SURVEY 8a row a1, 8f-3.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import torch
+
+from . import _lib
+
+
+def las_to_pixels(X: torch.Tensor, Y: torch.Tensor, Z: torch.Tensor, offsets: torch.Tensor, tiles: Sequence[dict],
+                  z_hi: float = 100.0, variant: str = "dataset") -> torch.Tensor:
+    """X, Y, Z: (ΣN) int32 CUDA tensors (the tiles' raw LAS coordinates, concatenated); offsets: (B + 1) int64 CUDA
+    tensor; tiles: per tile a dict with `scales` (3), `offsets` (3) (las.header) and, for the dataset variant,
+    `top_left` (2), `height`, `width`, optional `res_x` (default 0.25); the predict variant uses `height` = `width` =
+    224 and res 0.25 unless given.  Returns (ΣN, 3) float32 on the same device."""
+    if variant not in ("dataset", "predict"):
+        raise ValueError("variant must be 'dataset' or 'predict'")
+    if not (X.is_cuda and Y.is_cuda and Z.is_cuda and offsets.is_cuda):
+        raise RuntimeError("las_to_pixels runs on CUDA only (sm_100a); no CPU fallback")
+    if X.dtype != torch.int32 or Y.dtype != torch.int32 or Z.dtype != torch.int32 or offsets.dtype != torch.int64:
+        raise TypeError("X, Y, Z must be int32 and offsets int64")
+    B, total = offsets.numel() - 1, X.numel()
+    if len(tiles) != B or Y.numel() != total or Z.numel() != total:
+        raise ValueError("tiles / offsets / coordinate sizes disagree")
+    dev = X.device
+    arr = (_lib.LasTile * max(B, 1))()
+    for i, t in enumerate(tiles):
+        e = arr[i]
+        for k in range(3):
+            e.scale[k] = float(t["scales"][k])
+            e.offset[k] = float(t["offsets"][k])
+        if variant == "dataset":
+            e.left, e.top = float(t["top_left"][0]), float(t["top_left"][1])
+            e.res, e.height, e.width = float(t.get("res_x", 0.25)), float(t["height"]), float(t["width"])
+            e.origin_from_min, e.clip = 0, 1
+        else:
+            e.left = e.top = 0.0
+            e.res, e.height, e.width = float(t.get("res_x", 0.25)), float(t.get("height", 224)), float(t.get("width", 224))
+            e.origin_from_min, e.clip = 1, 0
+    meta = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+    out = torch.empty(total, 3, dtype=torch.float32, device=dev)
+    mm = torch.empty(4 * max(B, 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().p3p_las_to_pixels(X.contiguous().data_ptr(), Y.contiguous().data_ptr(), Z.contiguous().data_ptr(),
+                                          offsets.contiguous().data_ptr(), B, total, meta.data_ptr(), C.c_double(float(z_hi)),
+                                          mm.data_ptr(), out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "p3p_las_to_pixels")
+    return out

@@ -247,6 +247,32 @@ def test_vit_token_sequence_matches_oracle(cuda_device, prec):
     assert_close(a, r, TOL[prec], f"tokens {prec}")
 
 
+@pytest.mark.parametrize("variant", ["dataset", "predict"])
+def test_las_front_end_is_bit_exact(cuda_device, variant):
+    """raw LAS integers -> pixel-space fp32 points, bit for bit the numpy / sklearn loader."""
+    from pixelspointspolygons_b200 import las_to_pixels
+
+    rng = np.random.default_rng(11)
+    metas, Xs, Ys, Zs, refs = [], [], [], [], []
+    for i, n in enumerate((30_000, 1, 77_777, 5)):
+        left, top = 2_600_000.0 + 56.0 * i, 1_200_000.0 + 56.0 * i
+        sc, of = (0.001, 0.001, 0.001 if i != 2 else 0.01), (left - 3.0, top - 7.0, 400.0)
+        X = rng.integers(2_900, 59_100, n).astype(np.int32)   # a little beyond the 56 m tile on both sides
+        Y = rng.integers(6_900, 63_100, n).astype(np.int32)
+        Z = rng.integers(-5_000, 60_000, n).astype(np.int32) if i != 3 else np.full(n, 777, np.int32)
+        m = dict(scales=sc, offsets=of, top_left=(left, top), height=224, width=224)
+        metas.append(m); Xs.append(X); Ys.append(Y); Zs.append(Z)
+        refs.append(po.las_points_to_pixels(X, Y, Z, sc, of, top_left=(left, top), variant=variant))
+    offs = torch.tensor(np.concatenate([[0], np.cumsum([len(x) for x in Xs])]), dtype=torch.int64, device=cuda_device)
+    cat = lambda a: torch.from_numpy(np.concatenate(a)).to(cuda_device)
+    got = las_to_pixels(cat(Xs), cat(Ys), cat(Zs), offs, metas, z_hi=100.0, variant=variant).cpu().numpy()
+    ref = np.concatenate(refs)
+    assert got.shape == ref.shape
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), np.abs(got - ref).max()
+    if variant == "dataset":
+        assert got[:, :2].min() >= 0.0 and got[:, :2].max() <= 224.0
+
+
 def test_multi_wave_batch_with_dependent_launch(cuda_device):
     """40 tiles x 60k points = about 1000 ranking chunks, more than two waves of the voxelizer grid: the PFN grid is a
     programmatic dependent launch that may start while the voxelizer's last wave drains -- no deadlock, same results."""

@@ -180,3 +180,32 @@ def test_vit_tokens_is_cat_cls_plus_pos():
     assert torch.equal(t[:, 0], (cls[0, 0] + pos[0, 0]).expand(2, -1))
     assert torch.equal(t[1, 2], x[1, 1] + pos[0, 2])
 
+
+def test_las_loader_restatement_matches_sklearn_and_hand_values():
+    from sklearn.preprocessing import MinMaxScaler
+
+    rng = np.random.default_rng(3)
+    n = 500
+    X = rng.integers(100_000, 156_000, n).astype(np.int32)
+    Y = rng.integers(200_000, 256_000, n).astype(np.int32)
+    Z = rng.integers(40_000, 75_000, n).astype(np.int32)
+    scales, offs = (0.001, 0.001, 0.001), (2_600_000.0, 1_200_000.0, 0.0)
+    top_left = (2_600_100.0, 1_200_200.0)
+    got = po.las_points_to_pixels(X, Y, Z, scales, offs, top_left=top_left)
+    # literal reference code (p3_coco.py:79-96) on laspy-style float64 coordinates
+    pts = np.vstack((X * scales[0] + offs[0], Y * scales[1] + offs[1], Z * scales[2] + offs[2])).transpose()
+    pts[:, :2] = (pts[:, :2] - top_left) / 0.25
+    pts[:, 1] = 224 - pts[:, 1]
+    pts[:, -1] = MinMaxScaler(feature_range=(0, 100)).fit_transform(pts[:, -1].reshape(-1, 1)).squeeze()
+    pts = pts.astype(np.float32)
+    pts[:, 0] = np.clip(pts[:, 0], 0, 224)
+    pts[:, 1] = np.clip(pts[:, 1], 0, 224)
+    assert np.array_equal(got, pts)
+    assert got[:, 2].min() == 0.0 and abs(got[:, 2].max() - 100.0) < 1e-4
+    # predict variant: the tile's own minimum is the origin, no clipping
+    got2 = po.las_points_to_pixels(X, Y, Z, scales, offs, variant="predict")
+    assert got2[:, 0].min() == 0.0 and got2[:, 1].max() == 224.0
+    # degenerate z range: sklearn maps everything to feature_range[0]
+    flat = po.las_points_to_pixels(X[:5], Y[:5], np.full(5, 1234, np.int32), scales, offs, top_left=top_left)
+    assert np.all(flat[:, 2] == 0.0)
+
