@@ -128,7 +128,15 @@ typedef struct p3p_las_tile {
     double height, width;    /* img_info['height'], img_info['width'] (pixels) */
     int32_t origin_from_min; /* 1: the tile's own x / y minimum is the origin (predictor.py:126) */
     int32_t clip;            /* 1: clip x to [0, width], y to [0, height] (p3_coco.py:95-96) */
+    int32_t d4;              /* replayed D4 element on x, y (p3_coco.py:114-160): P3P_D4_NONE (not applied) or E ... T */
+    int32_t reserved;
+    double center_x, center_y; /* in_width // 2, in_height // 2: centre of the D4 transform */
 } p3p_las_tile;
+
+/* P3P_D4_E is the applied identity: like the reference it still moves the points to the centre and back (two float32
+ * roundings); P3P_D4_NONE leaves them untouched (transform not applied / not the training split). */
+enum { P3P_D4_NONE = 0, P3P_D4_E = 1, P3P_D4_R90 = 2, P3P_D4_R180 = 3, P3P_D4_R270 = 4, P3P_D4_V = 5, P3P_D4_HVT = 6,
+       P3P_D4_H = 7, P3P_D4_T = 8 };
 
 const char* p3p_last_error(void);
 int p3p_version(void);

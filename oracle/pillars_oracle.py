@@ -430,3 +430,35 @@ def las_points_to_pixels(X, Y, Z, scales, offsets, top_left=None, height=224, wi
         pts[:, 1] = np.clip(pts[:, 1], 0, height)
     return pts
 
+
+def apply_d4_to_lidar(lidar: np.ndarray, group_element: str, center=(112, 112)) -> np.ndarray:
+    """P3Dataset.apply_d4_augmentations_to_lidar (R:.../datasets/p3_coco.py:114-160) for an applied D4 transform:
+    float32 in-place arithmetic about the tile centre, statement by statement as the reference."""
+    lidar = np.array(lidar, dtype=np.float32, copy=True)
+    lidar[:, :2] -= center
+    if group_element == 'e':
+        pass
+    elif group_element == 'r90':
+        lidar[:, [0, 1]] = lidar[:, [1, 0]]
+        lidar[:, 1] = -lidar[:, 1]
+    elif group_element == 'r180':
+        lidar[:, 0] = -lidar[:, 0]
+        lidar[:, 1] = -lidar[:, 1]
+    elif group_element == 'r270':
+        lidar[:, [0, 1]] = lidar[:, [1, 0]]
+        lidar[:, 0] = -lidar[:, 0]
+    elif group_element == 'v':
+        lidar[:, 1] = -lidar[:, 1]
+    elif group_element == 'hvt':
+        lidar[:, [0, 1]] = lidar[:, [1, 0]]
+        lidar[:, 0] = -lidar[:, 0]
+        lidar[:, 1] = -lidar[:, 1]
+    elif group_element == 'h':
+        lidar[:, 0] = -lidar[:, 0]
+    elif group_element == 't':
+        lidar[:, [0, 1]] = lidar[:, [1, 0]]
+    else:
+        raise ValueError(f"Unknown group element {group_element}")
+    lidar[:, :2] += center
+    return lidar
+

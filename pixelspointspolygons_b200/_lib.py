@@ -22,7 +22,11 @@ EXPORTED = [
 class LasTile(C.Structure):
     _fields_ = [("scale", C.c_double * 3), ("offset", C.c_double * 3), ("left", C.c_double), ("top", C.c_double),
                 ("res", C.c_double), ("height", C.c_double), ("width", C.c_double), ("origin_from_min", C.c_int32),
-                ("clip", C.c_int32)]
+                ("clip", C.c_int32), ("d4", C.c_int32), ("reserved", C.c_int32), ("center_x", C.c_double),
+                ("center_y", C.c_double)]
+
+
+P3P_D4 = {None: 0, "none": 0, "e": 1, "r90": 2, "r180": 3, "r270": 4, "v": 5, "hvt": 6, "h": 7, "t": 8}
 
 
 class Grid(C.Structure):

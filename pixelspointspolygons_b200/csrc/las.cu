@@ -8,7 +8,8 @@
 //   x       = (x64 - left) / res;   y = height - (y64 - top) / res           (float64)
 //   z       = z64 * scale_ + min_   with sklearn's MinMaxScaler(feature_range = (0, z_hi)) fitted on the tile:
 //             scale_ = z_hi / (zmax - zmin) (range below 10 eps -> 1), min_ = 0 - zmin * scale_
-//   points  = float32(x, y, z);  dataset variant: x, y clipped to [0, width] / [0, height]
+//   points  = float32(x, y, z);  dataset variant: x, y clipped to [0, width] / [0, height]; optionally the replayed D4
+//             element of the training augmentation on x, y about the tile centre (float32, p3_coco.py:114-160)
 // Every float64 operation is a single IEEE operation in the reference's order (no FMA contraction), so the result is
 // bit-identical to the numpy path.  The tile's z extremes (and x / y minima for the predictor variant, whose origin is
 // the tile's minimum) are taken over the integers: the int -> float64 map is monotone for positive scales.
@@ -91,6 +92,22 @@ las_pixels_kernel(const int32_t* __restrict__ X, const int32_t* __restrict__ Y, 
         if (t.clip) {  // p3_coco.py:95-96 (np.clip on the float32 array)
             fx = fminf(fmaxf(fx, 0.f), (float)t.width);
             fy = fminf(fmaxf(fy, 0.f), (float)t.height);
+        }
+        if (t.d4 != P3P_D4_NONE) {  // apply_d4_augmentations_to_lidar (p3_coco.py:114-160), float32 like the reference
+            const float cx = (float)t.center_x, cy = (float)t.center_y;
+            const float ax = fx - cx, ay = fy - cy;
+            float bx = ax, by = ay;
+            switch (t.d4) {
+                case P3P_D4_R90: bx = ay; by = -ax; break;    // swap, then y = -y
+                case P3P_D4_R180: bx = -ax; by = -ay; break;
+                case P3P_D4_R270: bx = -ay; by = ax; break;   // swap, then x = -x
+                case P3P_D4_V: by = -ay; break;
+                case P3P_D4_HVT: bx = -ay; by = -ax; break;   // swap, then both negated
+                case P3P_D4_H: bx = -ax; break;
+                case P3P_D4_T: bx = ay; by = ax; break;
+                default: break;
+            }
+            fx = bx + cx; fy = by + cy;
         }
         out[i * 3 + 0] = fx; out[i * 3 + 1] = fy; out[i * 3 + 2] = fz;
     }

@@ -20,8 +20,10 @@ def las_to_pixels(X: torch.Tensor, Y: torch.Tensor, Z: torch.Tensor, offsets: to
                   z_hi: float = 100.0, variant: str = "dataset") -> torch.Tensor:
     """X, Y, Z: (ΣN) int32 CUDA tensors (the tiles' raw LAS coordinates, concatenated); offsets: (B + 1) int64 CUDA
     tensor; tiles: per tile a dict with `scales` (3), `offsets` (3) (las.header) and, for the dataset variant,
-    `top_left` (2), `height`, `width`, optional `res_x` (default 0.25); the predict variant uses `height` = `width` =
-    224 and res 0.25 unless given.  Returns (ΣN, 3) float32 on the same device."""
+    `top_left` (2), `height`, `width`, optional `res_x` (default 0.25) and optional `d4` (the replayed group element
+    'e', 'r90', 'r180', 'r270', 'v', 'hvt', 'h', 't' of the training augmentation when it was applied; absent / None: not
+    applied); the predict variant uses `height` =
+    `width` = 224 and res 0.25 unless given.  Returns (ΣN, 3) float32 on the same device."""
     if variant not in ("dataset", "predict"):
         raise ValueError("variant must be 'dataset' or 'predict'")
     if not (X.is_cuda and Y.is_cuda and Z.is_cuda and offsets.is_cuda):
@@ -46,6 +48,11 @@ def las_to_pixels(X: torch.Tensor, Y: torch.Tensor, Z: torch.Tensor, offsets: to
             e.left = e.top = 0.0
             e.res, e.height, e.width = float(t.get("res_x", 0.25)), float(t.get("height", 224)), float(t.get("width", 224))
             e.origin_from_min, e.clip = 1, 0
+        # replayed D4 element of the training augmentation (p3_coco.py:114-160): `d4` = group element name, centre =
+        # (in_width // 2, in_height // 2)
+        d4 = t.get("d4")
+        e.d4 = _lib.P3P_D4[d4 if d4 is None else str(d4)]
+        e.center_x, e.center_y = float(t.get("center", (int(e.width) // 2, int(e.height) // 2))[0]), float(t.get("center", (int(e.width) // 2, int(e.height) // 2))[1])
     meta = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
     out = torch.empty(total, 3, dtype=torch.float32, device=dev)
     mm = torch.empty(4 * max(B, 1), dtype=torch.int32, device=dev)

@@ -261,8 +261,12 @@ def test_las_front_end_is_bit_exact(cuda_device, variant):
         Y = rng.integers(6_900, 63_100, n).astype(np.int32)
         Z = rng.integers(-5_000, 60_000, n).astype(np.int32) if i != 3 else np.full(n, 777, np.int32)
         m = dict(scales=sc, offsets=of, top_left=(left, top), height=224, width=224)
+        r = po.las_points_to_pixels(X, Y, Z, sc, of, top_left=(left, top), variant=variant)
+        if variant == "dataset":  # training loader: the replayed D4 element follows (one of the 8 per tile)
+            m["d4"] = ("r90", "hvt", "v", "t")[i]
+            r = po.apply_d4_to_lidar(r, m["d4"])
         metas.append(m); Xs.append(X); Ys.append(Y); Zs.append(Z)
-        refs.append(po.las_points_to_pixels(X, Y, Z, sc, of, top_left=(left, top), variant=variant))
+        refs.append(r)
     offs = torch.tensor(np.concatenate([[0], np.cumsum([len(x) for x in Xs])]), dtype=torch.int64, device=cuda_device)
     cat = lambda a: torch.from_numpy(np.concatenate(a)).to(cuda_device)
     got = las_to_pixels(cat(Xs), cat(Ys), cat(Zs), offs, metas, z_hi=100.0, variant=variant).cpu().numpy()
@@ -271,6 +275,26 @@ def test_las_front_end_is_bit_exact(cuda_device, variant):
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), np.abs(got - ref).max()
     if variant == "dataset":
         assert got[:, :2].min() >= 0.0 and got[:, :2].max() <= 224.0
+
+
+def test_las_front_end_d4_elements(cuda_device):
+    """all eight D4 elements against the reference's statements (p3_coco.py:114-160)"""
+    from pixelspointspolygons_b200 import las_to_pixels
+
+    rng = np.random.default_rng(12)
+    names = ["e", "r90", "r180", "r270", "v", "hvt", "h", "t"]
+    n = 4000
+    X = rng.integers(0, 56_000, n).astype(np.int32); Y = rng.integers(0, 56_000, n).astype(np.int32)
+    Z = rng.integers(0, 30_000, n).astype(np.int32)
+    sc, of, tl = (0.001, 0.001, 0.001), (2_600_000.0, 1_200_000.0, 0.0), (2_600_000.0, 1_200_000.0)
+    base = po.las_points_to_pixels(X, Y, Z, sc, of, top_left=tl)
+    metas = [dict(scales=sc, offsets=of, top_left=tl, height=224, width=224, d4=g) for g in names]
+    offs = torch.arange(0, (len(names) + 1) * n, n, dtype=torch.int64, device=cuda_device)
+    rep = lambda a: torch.from_numpy(np.tile(a, len(names))).to(cuda_device)
+    got = las_to_pixels(rep(X), rep(Y), rep(Z), offs, metas).cpu().numpy().reshape(len(names), n, 3)
+    for k, g in enumerate(names):
+        ref = po.apply_d4_to_lidar(base, g)
+        assert np.array_equal(got[k].view(np.uint32), ref.view(np.uint32)), g
 
 
 def test_multi_wave_batch_with_dependent_launch(cuda_device):

@@ -209,3 +209,16 @@ def test_las_loader_restatement_matches_sklearn_and_hand_values():
     flat = po.las_points_to_pixels(X[:5], Y[:5], np.full(5, 1234, np.int32), scales, offs, top_left=top_left)
     assert np.all(flat[:, 2] == 0.0)
 
+
+def test_d4_replay_restatement_is_a_group_action():
+    pts = np.array([[10.0, 20.0, 3.0], [200.5, 7.25, 50.0]], dtype=np.float32)
+    r90 = po.apply_d4_to_lidar(pts, "r90")
+    assert np.allclose(r90[0, :2], [112 + (20 - 112), 112 - (10 - 112)])
+    four = pts
+    for _ in range(4):
+        four = po.apply_d4_to_lidar(four, "r90")
+    assert np.array_equal(four, pts)
+    assert np.array_equal(po.apply_d4_to_lidar(po.apply_d4_to_lidar(pts, "t"), "t"), pts)
+    assert np.array_equal(po.apply_d4_to_lidar(pts, "e"), pts)
+    assert np.array_equal(po.apply_d4_to_lidar(pts, "r180"), po.apply_d4_to_lidar(po.apply_d4_to_lidar(pts, "h"), "v"))
+
