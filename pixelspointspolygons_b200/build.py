@@ -9,7 +9,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-LIB_PATH = os.path.join(_HERE, "libp3p.so")
+# P3P_LIB selects another build of the same library (kernel experiments: tools/build_variant.py); the product default is in-tree
+LIB_PATH = os.environ.get("P3P_LIB") or os.path.join(_HERE, "libp3p.so")
 SOURCES = ["capi.cu", "voxelize.cu", "pfn.cu", "patch_embed.cu", "las.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -32,17 +33,18 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, out: str = None, extra_flags=None) -> str:
+    out = out or LIB_PATH
+    if out == LIB_PATH and not force and not is_stale():
         return LIB_PATH
-    extra = os.environ.get("P3P_EXTRA_NVCC_FLAGS", "").split()
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = list(extra_flags) if extra_flags is not None else os.environ.get("P3P_EXTRA_NVCC_FLAGS", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", INCLUDE, "-I", CSRC, "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

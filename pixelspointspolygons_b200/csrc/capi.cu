@@ -83,6 +83,14 @@ int make_grid(const p3p_grid* g, GridDev* out) {
     if (k < 0) return fail(P3P_ERR_UNSUPPORTED, "point_cloud_range magnitude %g too large", (double)maxabs);
     d.fix_scale = ldexpf(1.f, k);
     d.fix_inv = ldexpf(1.f, -k);
+    // single-word variant: |coordinate| * 2^k2 * M < 2^31 (the tensor-core kernel sums a pillar's slots in one int32);
+    // below 12 fractional bits the mean would lose accuracy against the fp32 contract -> not offered
+    int mbits = 0;
+    while ((1 << mbits) < g->max_points) ++mbits;
+    int k2 = 30 - mbits - (int)ceilf(log2f(maxabs + 1.f));
+    if (k2 > 20) k2 = 20;
+    d.fix2_scale = k2 >= 12 ? ldexpf(1.f, k2) : 0.f;
+    d.fix2_inv = k2 >= 12 ? ldexpf(1.f, -k2) : 0.f;
     *out = d;
     return P3P_OK;
 }
@@ -153,7 +161,7 @@ static int run_pfn(const PfnArgs& a, int precision, cudaStream_t st) {
     // The tensor-core kernel covers the shipped encoder configs and the low half of the density ablation (M <= 64: a
     // pillar always takes 64 operand rows, C <= 384); M > 64 takes the exact-fp32 kernel, which is at least as accurate
     // as either tensor-core contract.
-    if (a.g.M <= 64 && a.bl.MT <= 3) return launch_pfn_tc(a, precision, st);
+    if (a.g.M <= 64 && a.bl.MT <= 3 && a.g.fix2_scale > 0.f) return launch_pfn_tc(a, precision, st);
     return launch_pfn_simt(a, st);
 }
 

@@ -39,6 +39,7 @@ struct GridDev {
     int flags;
     float vx, vy, x_off, y_off;  // PillarFeatureNet: vx, vy, vx/2 + min_x, vy/2 + min_y
     float fix_scale, fix_inv;    // fixed-point grid of the cluster-mean sums (2^k, 2^-k): order-independent, exact
+    float fix2_scale, fix2_inv;  // coarser grid whose sum over M slots fits one int32 (tensor-core kernel); 0: not available
 };
 
 int make_grid(const p3p_grid* g, GridDev* out);
@@ -264,6 +265,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// the same on a precomputed 32-bit shared address (kept in a register: `opaque` stops the compiler from re-deriving it
+// from the thread index at every use)
+__device__ __forceinline__ uint32_t opaque(uint32_t x) {
+    asm volatile("" : "+r"(x));
+    return x;
+}
+__device__ __forceinline__ void mbar_arrive_sa(uint32_t bar) {
+    asm volatile("{.reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0];}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_sa(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sa(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait_sa(bar, parity)) {
+    }
+}
+__device__ __forceinline__ uint32_t mbar_test_sa(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{.reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -324,6 +356,36 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t taddr, float (&v)[32]) {
         : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15]),"=f"(v[16]),"=f"(v[17]),"=f"(v[18]),"=f"(v[19]),"=f"(v[20]),"=f"(v[21]),"=f"(v[22]),"=f"(v[23]),"=f"(v[24]),"=f"(v[25]),"=f"(v[26]),"=f"(v[27]),"=f"(v[28]),"=f"(v[29]),"=f"(v[30]),"=f"(v[31])
         : "r"(taddr)
         : "memory");
+}
+
+// Split form for software pipelining inside a warp: issue a load, then later wait for every outstanding load of the
+// thread.  The wait lists the registers of the load(s) it completes as in/out operands so that no consumer can be
+// scheduled above it; ptxas tracks tcgen05.ld with a scoreboard, so arithmetic on registers of an EARLIER, already
+// awaited load overlaps with a load that is still in flight.
+#define P3P_R32(v)                                                                                                        \
+    "+f"(v[0]),"+f"(v[1]),"+f"(v[2]),"+f"(v[3]),"+f"(v[4]),"+f"(v[5]),"+f"(v[6]),"+f"(v[7]),"+f"(v[8]),"+f"(v[9]),"+f"(v[10]),   \
+    "+f"(v[11]),"+f"(v[12]),"+f"(v[13]),"+f"(v[14]),"+f"(v[15]),"+f"(v[16]),"+f"(v[17]),"+f"(v[18]),"+f"(v[19]),"+f"(v[20]),    \
+    "+f"(v[21]),"+f"(v[22]),"+f"(v[23]),"+f"(v[24]),"+f"(v[25]),"+f"(v[26]),"+f"(v[27]),"+f"(v[28]),"+f"(v[29]),"+f"(v[30]),    \
+    "+f"(v[31])
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15]),"=f"(v[16]),"=f"(v[17]),"=f"(v[18]),"=f"(v[19]),"=f"(v[20]),"=f"(v[21]),"=f"(v[22]),"=f"(v[23]),"=f"(v[24]),"=f"(v[25]),"=f"(v[26]),"=f"(v[27]),"=f"(v[28]),"=f"(v[29]),"=f"(v[30]),"=f"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : P3P_R32(v) : : "memory");
+}
+// non-blocking probe of an mbarrier phase (the result is consumed later: its latency hides behind independent work)
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{.reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
 }
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {

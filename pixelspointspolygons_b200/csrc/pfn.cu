@@ -360,14 +360,16 @@ constexpr int kTcThreads = 32 * (kEpiWarp0 + 4 * kEpiGroups);
 #ifndef P3P_REG_MMA
 #define P3P_REG_MMA 40
 #define P3P_REG_FRONT 104
-#define P3P_REG_EPI 72
+#define P3P_REG_EPI 88
 #endif
 constexpr int kRegMma = P3P_REG_MMA, kRegFront = P3P_REG_FRONT, kRegEpi = P3P_REG_EPI;  // registers per thread after setmaxnreg (launch: 80)
-static_assert(4 * kRegMma + 8 * kRegFront + 12 * kRegEpi <= 24 * 80, "register pool of the launch exceeded");
+static_assert(4 * kRegMma + 8 * kRegFront + 12 * kRegEpi <= 2048, "register file of the SM exceeded (65536 / 32 lanes)");
 constexpr int kUnit = 8;                       // items per unit = 4 pillar pairs, consecutive canvas cells
 constexpr int kPairsPerUnit = kUnit / 2;
-constexpr int kTmemStage = 144;                // TMEM columns per accumulator stage: 128 (pillar pair) + 16 (W1b' hmax of the pair)
-constexpr int kTmemStages = 3;                 // ring of accumulator stages shared by the epilogue groups
+constexpr int kTiles = 3;                      // 128-channel MMA tiles (C <= 384)
+constexpr int kAccCols = 64;                   // TMEM columns of one accumulator stage: one pillar (64 operand rows)
+constexpr int kAccStages = 2;                  // accumulator stages per channel tile: the issuer refills one while the epilogue drains the other
+constexpr int kGCol0 = kTiles * kAccStages * kAccCols;  // first of the 3 x 16 columns holding W1b' hmax of a unit (384 + 16 m)
 constexpr int kValidRing = 64;               // pairs of validity flags in flight between front end and epilogue (>= kNS + ring slack)
 constexpr int kStageRows = 128;                // operand rows of a pair: 2 x 64 slots
 
@@ -385,7 +387,7 @@ struct TcCfg {
     static constexpr int kNS = kTf32 ? P3P_NS_TF32 : P3P_NS_16;            // B-operand stages: pillar pairs in flight
     static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * kHStage + 2 * (size_t)kGStage;
     static constexpr size_t kSmemFloats = 10 * 32 + 384 + kNF * 128 * 4;
-    static constexpr size_t kSmemBytes = 1024 + kSmemOperands + kSmemFloats * 4 + (2 * kNS + 4 * kTmemStages + 2 + 2) * 8 + 16 + 2 * kNF * 4 + 2 * kValidRing;
+    static constexpr size_t kSmemBytes = kSmemOperands + kSmemFloats * 4 + (2 * kNS + 2 * kTiles * kAccStages + 2 * kTiles + 2 + 2) * 8 + 16 + 2 * kNF * 4 + 2 * kValidRing + 4 * kEpiGroups * kUnit * 32 * 4;
 };
 
 
@@ -472,9 +474,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     using Cfg = TcCfg<kPrec>;
     constexpr bool kTf32 = Cfg::kTf32;
     constexpr int kNS = Cfg::kNS;
-    extern __shared__ unsigned char smem_dyn[];
-    const uint32_t raw = smem_u32(smem_dyn);
-    unsigned char* base = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
+    // The kernel has no static shared memory, so the dynamic block starts at shared-memory offset 0 of the CTA window and
+    // the declared alignment holds (checked below): every shared address below is a compile-time offset.
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    unsigned char* base = smem_dyn;
     unsigned char* sA1 = base;
     unsigned char* sA2 = sA1 + 3 * Cfg::kATile;
     unsigned char* sH = sA2 + 3 * Cfg::kATile;                          // [kNS][128 rows]
@@ -485,14 +488,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPts + kNF * 128);
     uint64_t* h_full = bars;                  // [kNS] front end -> MMA (2 arrivals: the two warps of a pair)
     uint64_t* h_empty = bars + kNS;           // [kNS] MMA -> front end (one tcgen05.commit per channel tile)
-    uint64_t* t_full = bars + 2 * kNS;        // [3] MMA warp m -> epilogue group m (tcgen05.commit), per pair
-    uint64_t* t_empty = t_full + kTmemStages; // [3] epilogue group m -> MMA warp m (128 arrivals)
-    uint64_t* gt_full = t_empty + kTmemStages;  // [3] MMA warp m -> epilogue group m, per unit (W1b' hmax accumulator)
-    uint64_t* gt_empty = gt_full + kTmemStages; // [3] epilogue group m -> MMA warp m (128 arrivals)
-    uint64_t* g_empty = gt_empty + kTmemStages; // [2] MMA warps -> front end: hmax rows of the unit slot consumed (MT commits)
+    uint64_t* t_full = bars + 2 * kNS;                  // [3 tiles][2 stages] MMA warp m -> epilogue group m (tcgen05.commit), per pillar
+    uint64_t* t_empty = t_full + kTiles * kAccStages;   // [3][2] epilogue group m -> MMA warp m (128 arrivals)
+    uint64_t* gt_full = t_empty + kTiles * kAccStages;  // [3] MMA warp m -> epilogue group m, per unit (W1b' hmax accumulator)
+    uint64_t* gt_empty = gt_full + kTiles;              // [3] epilogue group m -> MMA warp m (128 arrivals)
+    uint64_t* g_empty = gt_empty + kTiles;              // [2] MMA warps -> front end: hmax rows of the unit slot consumed (MT commits)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_empty + 2);
     int* sDesc = reinterpret_cast<int*>(tmem_slot + 2);                 // [kNF][2] descriptor word of the item decoded next
     unsigned char* sValid = reinterpret_cast<unsigned char*>(sDesc + 2 * kNF);  // [kValidRing pairs][2]: the item holds a pillar
+    float* sRmax = reinterpret_cast<float*>(sValid + 2 * kValidRing);           // [12 epilogue warps][kUnit][32]: pillar maxima of the unit in work
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int MT = a.bl.MT;
@@ -503,13 +507,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     const bool canvas = (kMode != 0) || (a.item_mode == kItemsCanvas);
 
     // ---- one-time setup --------------------------------------------------------------------------
+    if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();  // the swizzled operand tiles need 1024-byte alignment
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
         for (int i = 0; i < kNS; ++i) { mbar_init(&h_full[i], 2); mbar_init(&h_empty[i], (uint32_t)MT); }
-        for (int i = 0; i < kTmemStages; ++i) {
-            mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128);
-            mbar_init(&gt_full[i], 1); mbar_init(&gt_empty[i], 128);
-        }
+        for (int i = 0; i < kTiles * kAccStages; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
+        for (int i = 0; i < kTiles; ++i) { mbar_init(&gt_full[i], 1); mbar_init(&gt_empty[i], 128); }
         mbar_init(&g_empty[0], (uint32_t)MT); mbar_init(&g_empty[1], (uint32_t)MT);
         fence_mbar_init();
     }
@@ -551,30 +554,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         const int m = warp;
         if (m < MT) {
             const bool leader = elect_one();
-            const uint32_t idesc_main = make_idesc(Cfg::kFmt, 128, 128);
+            const uint32_t idesc_main = make_idesc(Cfg::kFmt, 128, kAccCols);
             const uint32_t idesc_g = make_idesc(Cfg::kFmt, 128, 16);
             const uint32_t desc_hi = (Cfg::kSBO >> 4) | (1u << 14) | (Cfg::kLayout << 29);
             const uint32_t a1_lo = ((smem_u32(sA1) + (uint32_t)(m * Cfg::kATile)) >> 4) | (1u << 16);
             const uint32_t a2_lo = ((smem_u32(sA2) + (uint32_t)(m * Cfg::kATile)) >> 4) | (1u << 16);
             const uint32_t h_lo = (smem_u32(sH) >> 4) | (1u << 16), g_lo = (smem_u32(sG) >> 4) | (1u << 16);
-            const uint32_t d_main = tmem_base + (uint32_t)(m * kTmemStage);
+            const uint32_t d_tile = tmem_base + (uint32_t)(m * kAccStages * kAccCols);
+            const uint32_t d_g = tmem_base + (uint32_t)(kGCol0 + m * 16);
+            uint64_t* tf = t_full + m * kAccStages;
+            uint64_t* te = t_empty + m * kAccStages;
             int st = 0;
             uint32_t use = 0;
             for (int p = 0; p < my_pairs; ++p) {
                 mbar_wait(&h_full[st], use & 1);
                 if (m == 0) PTL(0, p, 0);
-                tc_fence_after();
                 const uint32_t hs_lo = h_lo + (uint32_t)st * (Cfg::kHStage >> 4);
-                {
-                    mbar_wait(&t_empty[m], ((uint32_t)p & 1u) ^ 1u);
-                    if (m == 0) PTL(0, p, 1);
+                // the pair's two pillars go to the tile's two accumulator stages: while the epilogue drains stage 1 of pair
+                // p - 1, stage 0 is already being refilled with pillar A of pair p
+#pragma unroll
+                for (int s = 0; s < kAccStages; ++s) {
+                    mbar_wait(&te[s], ((uint32_t)p & 1u) ^ 1u);
+                    if (m == 0 && s == 0) PTL(0, p, 1);
                     tc_fence_after();
                     if (leader) {
+                        const uint32_t b_lo = hs_lo + (uint32_t)(s * ((64 * Cfg::RB) >> 4));  // rows 64 s .. 64 s + 63 of the stage
 #pragma unroll
                         for (int k = 0; k < Cfg::kKSteps; ++k)
-                            tc_mma<kTf32>(d_main, ((uint64_t)desc_hi << 32) | (a1_lo + (uint32_t)(k * 2)),
-                                          ((uint64_t)desc_hi << 32) | (hs_lo + (uint32_t)(k * 2)), idesc_main, k > 0);
-                        tc_commit(&t_full[m]);
+                            tc_mma<kTf32>(d_tile + (uint32_t)(s * kAccCols), ((uint64_t)desc_hi << 32) | (a1_lo + (uint32_t)(k * 2)),
+                                          ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)(k * 2)), idesc_main, k > 0);
+                        tc_commit(&tf[s]);
                     }
                     __syncwarp();
                 }
@@ -592,7 +601,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                         const uint32_t gs_lo = g_lo + slot * (Cfg::kGStage >> 4);
 #pragma unroll
                         for (int k = 0; k < Cfg::kKSteps; ++k)
-                            tc_mma<kTf32>(d_main + 128, ((uint64_t)desc_hi << 32) | (a2_lo + (uint32_t)(k * 2)),
+                            tc_mma<kTf32>(d_g, ((uint64_t)desc_hi << 32) | (a2_lo + (uint32_t)(k * 2)),
                                           ((uint64_t)desc_hi << 32) | (gs_lo + (uint32_t)(k * 2)), idesc_g, k > 0);
                         tc_commit(&gt_full[m]);
                         tc_commit(&g_empty[slot]);
@@ -617,7 +626,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             uy[i] = *reinterpret_cast<const float2*>(sFront + 1 * 32 + 8 * o + 2 * i);
             uz[i] = *reinterpret_cast<const float2*>(sFront + 2 * 32 + 8 * o + 2 * i);
         }
-        const float* kc = sFront + 8 * o;  // rows 3..9 of the lane's 8 channels
+        const float* kc = sFront + 8 * o;  // row 9 (relu(b0) of a padded slot) of the lane's 8 channels
+        // rows 3..8 of channel `lane`: the per-pillar constant kappa is computed one channel per lane
+        const float k_cx = sFront[3 * 32 + lane], k_cy = sFront[4 * 32 + lane], k_mx = sFront[5 * 32 + lane];
+        const float k_my = sFront[6 * 32 + lane], k_mz = sFront[7 * 32 + lane], k_b0 = sFront[8 * 32 + lane];
         float4* pbuf = sPts + fw * 128;    // [2 sets][64]
         const uint32_t pbuf_sa = smem_u32(pbuf);
         // byte offset of the lane's first slot inside a stage: row (half * 64 + pt), the lane's chunk(s) under the swizzle
@@ -696,21 +708,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             if (it.valid) {
                 const int n = it.n;
                 const float4* P = pbuf + (j & 1) * 64;
-                // cluster mean on the fixed-point grid (exact integer sums: independent of the order); lane c < 3 turns
-                // the sums of coordinate c into the mean
-                float mean_o;
+                // cluster mean on the fixed-point grid (exact integer sums: independent of the order of the slots);
+                // rows beyond n are zero-filled by the copy.  |q| * 64 slots < 2^31 (fix2_scale is sized for M).
+                float mpx, mpy, mz;
                 {
                     const float4 s0 = P[lane], s1 = P[lane + 32];
-                    int lo0, hi0, lo1, hi1, sl[3], sh[3];
-                    fix_split(s0.x, a.g.fix_scale, lo0, hi0); fix_split(s1.x, a.g.fix_scale, lo1, hi1);
-                    sl[0] = __reduce_add_sync(0xffffffffu, lo0 + lo1); sh[0] = __reduce_add_sync(0xffffffffu, hi0 + hi1);
-                    fix_split(s0.y, a.g.fix_scale, lo0, hi0); fix_split(s1.y, a.g.fix_scale, lo1, hi1);
-                    sl[1] = __reduce_add_sync(0xffffffffu, lo0 + lo1); sh[1] = __reduce_add_sync(0xffffffffu, hi0 + hi1);
-                    fix_split(s0.z, a.g.fix_scale, lo0, hi0); fix_split(s1.z, a.g.fix_scale, lo1, hi1);
-                    sl[2] = __reduce_add_sync(0xffffffffu, lo0 + lo1); sh[2] = __reduce_add_sync(0xffffffffu, hi0 + hi1);
-                    const int msl = (o == 0) ? sl[0] : ((o == 1) ? sl[1] : sl[2]);
-                    const int msh = (o == 0) ? sh[0] : ((o == 1) ? sh[1] : sh[2]);
-                    mean_o = fix_mean(msl, msh, a.g.fix_inv, (float)n);
+                    const float fs = a.g.fix2_scale;
+                    const int sx = __reduce_add_sync(0xffffffffu, __float2int_rn(s0.x * fs) + __float2int_rn(s1.x * fs));
+                    const int sy = __reduce_add_sync(0xffffffffu, __float2int_rn(s0.y * fs) + __float2int_rn(s1.y * fs));
+                    const int sz = __reduce_add_sync(0xffffffffu, __float2int_rn(s0.z * fs) + __float2int_rn(s1.z * fs));
+                    const float wn = __fdividef(a.g.fix2_inv, (float)n);
+                    mpx = (float)sx * wn - it.ctr_x;
+                    mpy = (float)sy * wn - it.ctr_y;
+                    mz = (float)sz * wn;
                 }
                 float qx[8], qy[8], qz[8];
 #pragma unroll
@@ -718,20 +728,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                     const float4 q = P[pt + 8 * i];
                     qx[i] = q.x - it.ctr_x; qy[i] = q.y - it.ctr_y; qz[i] = q.z;
                 }
-                const float mpx = __shfl_sync(0xffffffffu, mean_o, 0) - it.ctr_x;
-                const float mpy = __shfl_sync(0xffffffffu, mean_o, 1) - it.ctr_y;
-                const float mz = __shfl_sync(0xffffffffu, mean_o, 2);
+                // per-pillar constant of channel `lane` (one channel per lane), then the lane's 8 channels by shuffle
                 float2 kap[4];
+                {
+                    float kl = __fmaf_rn(k_cx, it.ctr_x, k_b0);
+                    kl = __fmaf_rn(k_cy, it.ctr_y, kl);
+                    kl = __fmaf_rn(k_mx, -mpx, kl);
+                    kl = __fmaf_rn(k_my, -mpy, kl);
+                    kl = __fmaf_rn(k_mz, -mz, kl);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 kcx = *reinterpret_cast<const float2*>(kc + 3 * 32 + 2 * i), kcy = *reinterpret_cast<const float2*>(kc + 4 * 32 + 2 * i);
-                    const float2 wmx = *reinterpret_cast<const float2*>(kc + 5 * 32 + 2 * i), wmy = *reinterpret_cast<const float2*>(kc + 6 * 32 + 2 * i);
-                    const float2 wmz = *reinterpret_cast<const float2*>(kc + 7 * 32 + 2 * i), b0v = *reinterpret_cast<const float2*>(kc + 8 * 32 + 2 * i);
-                    float2 t = ffma2(kcx, make_float2(it.ctr_x, it.ctr_x), b0v);
-                    t = ffma2(kcy, make_float2(it.ctr_y, it.ctr_y), t);
-                    t = ffma2(wmx, make_float2(-mpx, -mpx), t);
-                    t = ffma2(wmy, make_float2(-mpy, -mpy), t);
-                    kap[i] = ffma2(wmz, make_float2(-mz, -mz), t);
+                    for (int i = 0; i < 4; ++i)
+                        kap[i] = make_float2(__shfl_sync(0xffffffffu, kl, 8 * o + 2 * i), __shfl_sync(0xffffffffu, kl, 8 * o + 2 * i + 1));
                 }
                 const uint32_t stage_sa = smem_u32(sH) + (uint32_t)st * Cfg::kHStage;
                 if constexpr (kTf32) {
@@ -839,6 +846,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     } else {
         // =========================== epilogue: group g owns channel tile g ===========================
         if constexpr (kRegEpi < 80) setmaxnreg_dec<kRegEpi>();
+        if constexpr (kRegEpi > 80) setmaxnreg_inc<kRegEpi>();
         const int g = (warp - kEpiWarp0) >> 2;
         const int quad = warp & 3;  // TMEM lanes this warp may read: 32 * (warp id % 4)
         const bool nchw = (kMode == 2) || (kMode == 0 && canvas && (a.out_layout == P3P_LAYOUT_NCHW));
@@ -858,40 +866,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         const int m = g;  // group g reads accumulator stage g = channel tile g
         const float bb = (m == 0) ? b1v[0] : ((m == 1) ? b1v[1] : b1v[2]);
         const int c = m * 128 + cl;
-        const uint32_t taddr = tlane + (uint32_t)(g * kTmemStage);
+        const uint32_t taddr = tlane + (uint32_t)(g * kAccStages * kAccCols);
+        const uint32_t gaddr = tlane + (uint32_t)(kGCol0 + g * 16);
+        const uint32_t tf_sa = opaque(smem_u32(t_full + g * kAccStages));   // stage s: + 8 s
+        const uint32_t te_sa = opaque(smem_u32(t_empty + g * kAccStages));
+        const uint32_t gtf_sa = opaque(smem_u32(gt_full + g)), gte_sa = opaque(smem_u32(gt_empty + g));
+        const int my_pillars = (g < MT) ? my_units * kUnit : 0;
         int jn = 0;
+        // Pillar q of the CTA sits in accumulator stage q & 1 of the tile; its barrier phase is (q >> 1) & 1.  The probe of
+        // the NEXT pillar's barrier is issued before the arithmetic on the current one, so that in the steady state (the
+        // issuer runs ahead) no wait is exposed.
+        uint32_t ready = 0;
+        float* my_rmax = sRmax + (warp - kEpiWarp0) * (kUnit * 32) + lane;  // [kUnit][32 lanes] strip of this warp
+        const uint32_t taddr_o = opaque(taddr);
         for (int j = 0; j < (g < MT ? my_units : 0); ++j) {
             const int ub = wu.b, ur = wu.r;  // tile / position of the unit's first item
             const int item0 = unit_item0;
             wu.step();
             unit_item0 += (int)gridDim.x * kUnit;
-            // ---- the unit's 4 pairs: max over each pillar's 64 accumulator columns -----------------------------------
+            // ---- the unit's 8 pillars: max over each pillar's 64 accumulator columns ---------------------------------
+            // (a rolled loop over the pairs: the 32-register blocks of the two loads keep one assignment; the pillar
+            // maxima wait for the unit's W1b' hmax term in a per-warp shared-memory strip, not in registers)
+#pragma unroll 1
+            for (int pr = 0; pr < kPairsPerUnit; ++pr) {
+#pragma unroll
+                for (int s = 0; s < kAccStages; ++s, ++jn) {
+                    const uint32_t tph = (uint32_t)(jn >> 1) & 1u;
+                    float va[32], vb[32];
+                    if (quad == 0) PTL(9 + g, jn, 0);
+                    if (!ready) mbar_wait_sa(tf_sa + 8u * s, tph);
+                    if (quad == 0) PTL(9 + g, jn, 1);
+                    tc_fence_after();
+                    tmem_ld32_issue(taddr_o + (uint32_t)(s * kAccCols), va);
+                    tmem_ld_wait(va);
+                    tmem_ld32_issue(taddr_o + (uint32_t)(s * kAccCols + 32), vb);
+                    ready = (jn + 1 < my_pillars) ? mbar_test_sa(tf_sa + 8u * (s ^ 1), (uint32_t)((jn + 1) >> 1) & 1u) : 0u;
+                    const float r0 = max32(va);
+                    tmem_ld_wait(vb);
+                    tc_fence_before();
+                    mbar_arrive_sa(te_sa + 8u * s);
+                    my_rmax[(2 * pr + s) * 32] = fmaxf(r0, max32(vb));
+                    if (quad == 0) PTL(9 + g, jn, 2);
+                }
+            }
             float rmax[kUnit];
 #pragma unroll
-            for (int pr = 0; pr < kPairsPerUnit; ++pr, ++jn) {
-                const uint32_t tph = (uint32_t)(j * kPairsPerUnit + pr) & 1u;
-                float va[32], vb[32];
-                if (quad == 0) PTL(9 + g, jn, 0);
-                mbar_wait(&t_full[g], tph);
-                if (quad == 0) PTL(9 + g, jn, 1);
-                tc_fence_after();
-                tmem_ld32_wait(taddr, va);
-                tmem_ld32_wait(taddr + 32, vb);
-                rmax[2 * pr] = fmaxf(max32(va), max32(vb));
-                tmem_ld32_wait(taddr + 64, va);
-                tmem_ld32_wait(taddr + 96, vb);
-                tc_fence_before();
-                mbar_arrive(&t_empty[g]);
-                rmax[2 * pr + 1] = fmaxf(max32(va), max32(vb));
-                if (quad == 0) PTL(9 + g, jn, 2);
-            }
+            for (int i = 0; i < kUnit; ++i) rmax[i] = my_rmax[i * 32];
             // ---- W1b' hmax of the unit's 8 items (one MMA per unit), bias, relu, the 8 cells ---------------------------
             float gv[8];
-            mbar_wait(&gt_full[g], (uint32_t)j & 1u);
+            mbar_wait_sa(gtf_sa, (uint32_t)j & 1u);
             tc_fence_after();
-            tmem_ld8_wait(taddr + 128, gv);
+            tmem_ld8_wait(gaddr, gv);
             tc_fence_before();
-            mbar_arrive(&gt_empty[g]);
+            mbar_arrive_sa(gte_sa);
             // which items hold a pillar: written by the front end before the pairs' operands were released
             const uint2 vv = *reinterpret_cast<const uint2*>(sValid + ((j * kPairsPerUnit) & (kValidRing - 1)) * 2);
             float ob[kUnit];

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 from oracle import pillars_oracle as po
 from pixelspointspolygons_b200 import PointPillarsEncoder, _lib, default_cfg
 
-prec = sys.argv[1] if len(sys.argv) > 1 else "tf32"
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp16"
 B, N = 16, 100_000
 dev = torch.device("cuda:0")
 cfg = default_cfg(device="cuda:0", p3p_precision=prec)
@@ -36,19 +36,22 @@ for cta in range(2):
     t0 = a[a > 0].min()
     a = np.where(a > 0, a - t0, -1)
     print(f"==== CTA {cta} ({prec}); cycles relative to the first stamp")
-    print("MMA: pair: h_full_ok, t_empty_ok (first tile), issued")
-    for p in list(range(0, 10)) + list(range(30, 44)):
+    print("MMA warp 0: pair: h_full_ok, t_empty[0]_ok, issued")
+    for p in list(range(0, 8)) + list(range(36, 44)):
         print(f"  p={p:3d} ", a[0, p, :3].tolist())
-    print("front end warp 0 / 1: j: loop_top, h_empty_ok, computed")
-    for j in list(range(0, 4)) + list(range(8, 12)):
+    print("front end warp 0 / 1: unit: loop_top, h_empty_ok, computed")
+    for j in list(range(0, 3)) + list(range(8, 11)):
         print(f"  j={j:3d} ", a[1, j, :3].tolist(), a[2, j, :3].tolist())
-    print("epilogue group 0 / 1 lead warp: job: wait_begin, t_full_ok, loads_done, stored")
-    for gp in list(range(0, 8)) + list(range(36, 44)):
-        print(f"  job={gp:3d} ", a[9, gp, :4].tolist(), a[10, gp, :4].tolist(), a[11, gp, :4].tolist())
+    print("epilogue group 0 / 1 / 2 lead warp: pillar: wait_begin, t_full_ok, drained")
+    for gp in list(range(0, 10)) + list(range(76, 88)):
+        print(f"  q={gp:3d} ", a[9, gp, :3].tolist(), a[10, gp, :3].tolist(), a[11, gp, :3].tolist())
     mm = a[0, :, 0]
     ok = mm > 0
     d = np.diff(mm[ok])
     print("MMA pair period: median", np.median(d), "p10", np.percentile(d, 10), "p90", np.percentile(d, 90), "pairs", ok.sum(), "last", mm[ok].max())
+    wt = a[0, :, 1] - a[0, :, 0]
+    iss = a[0, :, 2] - a[0, :, 1]
+    print("MMA warp 0: wait t_empty[0] median", np.median(wt[ok]), " issue (both stages incl. t_empty[1] wait) median", np.median(iss[ok]))
     for r in range(1, 9):
         c = a[r, :, 2] - a[r, :, 1]
         w = a[r, :, 1] - a[r, :, 0]
@@ -59,5 +62,5 @@ for cta in range(2):
         okr = a[r, :, 2] > 0
         w = a[r, :, 1] - a[r, :, 0]
         ld = a[r, :, 2] - a[r, :, 1]
-        stt = a[r, :, 3] - a[r, :, 2]
-        print(f"epi group {r-9}: wait t_full median {np.median(w[okr]):.0f}  loads median {np.median(ld[okr]):.0f}  store median {np.median(stt[okr]):.0f}  jobs {okr.sum()}  last {a[r, :, 3].max()}")
+        per = np.diff(a[r, :, 2][okr])
+        print(f"epi group {r-9}: wait t_full median {np.median(w[okr]):.0f}  drain median {np.median(ld[okr]):.0f}  pillar period median {np.median(per):.0f}  pillars {okr.sum()}  last {a[r, :, 2].max()}")
