@@ -73,6 +73,9 @@ int make_grid(const p3p_grid* g, GridDev* out) {
         return fail(P3P_ERR_INVALID_ARGUMENT, "scatter output_shape (%d, %d) smaller than the voxel grid (%d, %d)", d.ny, d.nx, d.nv[1], d.nv[0]);
     d.vx = g->voxel_size[0];
     d.vy = g->voxel_size[1];
+    if (voxelize_smem_bytes(d) > kVoxelizeMaxSmem)
+        return fail(P3P_ERR_UNSUPPORTED, "grid of %d keys and a %d x %d canvas needs %zu bytes of shared memory per CTA (limit %zu)",
+                    d.num_keys, d.ny, d.nx, voxelize_smem_bytes(d), kVoxelizeMaxSmem);
     d.x_off = g->voxel_size[0] / 2 + g->range_min[0];
     d.y_off = g->voxel_size[1] / 2 + g->range_min[1];
     // fixed-point grid of the cluster-mean sums: |coordinate| * 2^k < 2^30, k <= 20
@@ -104,11 +107,12 @@ int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out)
     int64_t denom = target - B;
     if (denom < 64) denom = 64;
     int64_t S = (total_points + denom - 1) / denom;
-    S = (S + 255) / 256 * 256;
+    S = (S + 1023) / 1024 * 1024;  // every lane owns whole groups of 4 points
     if (S < 1024) S = 1024;
     if (S > kMaxChunkPoints) S = kMaxChunkPoints;
     l.chunk_points = (int)S;
-    const int64_t mc = total_points / S + B;
+    // chunks of a tile start at its first point rounded down to a multiple of 4: sum_b ceil((n_b + 3) / S) <= this
+    const int64_t mc = (total_points + 3 * (int64_t)B) / S + B;
     if (mc > 0x7fffffff) return fail(P3P_ERR_UNSUPPORTED, "too many ranking chunks");
     l.max_chunks = (int)mc;
     size_t off = 0;
@@ -118,7 +122,7 @@ int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out)
         return o;
     };
     const size_t HW = (size_t)g.ny * g.nx;
-    const size_t sync_words = ((size_t)(1 + l.max_chunks + B) * sizeof(unsigned) + 15) / 16 * 16;
+    const size_t sync_words = ((size_t)(1 + l.max_chunks + 2 * B) * sizeof(unsigned) + 15) / 16 * 16;
     l.sync_bytes = sync_words + (size_t)B * g.num_keys;  // ticket / flags / tile_done, then the edge flags: one memset
     l.off_sync = take(l.sync_bytes);
     l.off_edge = l.off_sync + sync_words;

@@ -49,10 +49,10 @@ int make_grid(const p3p_grid* g, GridDev* out);
 // ----------------------------------------------------------------------------------------------
 struct WsLayout {
     int B;
-    int chunk_points;      // S: points per ranking chunk (multiple of 256, <= kMaxChunkPoints)
+    int chunk_points;      // S: points per ranking chunk (multiple of 1024, <= kMaxChunkPoints)
     int max_chunks;        // upper bound of the number of chunks over the batch (= grid of the voxelize kernel)
     int key_stride;        // chunk_hist row stride (elements)
-    size_t off_sync;       // uint32 ticket, flags[max_chunks], tile_done[B], then uint8 edge[B][num_keys]
+    size_t off_sync;       // uint32 ticket, flags[max_chunks], tile_done[B], tile_sat[B], then uint8 edge[B][num_keys]
     size_t sync_bytes;     //   (one block, zeroed at the start of every call)
     size_t off_edge;       // uint8 [B][num_keys]: the run of this key holds a point on the x / y max face (cell == extent),
                            //   i.e. its coordinates are not decodable from the key (hash aliasing)
@@ -71,6 +71,8 @@ struct WsLayout {
 };
 
 int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out);
+constexpr size_t kVoxelizeMaxSmem = 200 * 1024;  // dynamic shared memory the voxelize kernel may opt in to
+size_t voxelize_smem_bytes(const GridDev& g);
 
 struct WsPtrs {
     unsigned* sync;
@@ -376,6 +378,19 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) 
 }
 __device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" : P3P_R32(v) : : "memory");
+}
+#define P3P_R16(v)                                                                                                        \
+    "+f"(v[0]),"+f"(v[1]),"+f"(v[2]),"+f"(v[3]),"+f"(v[4]),"+f"(v[5]),"+f"(v[6]),"+f"(v[7]),"+f"(v[8]),"+f"(v[9]),"+f"(v[10]),   \
+    "+f"(v[11]),"+f"(v[12]),"+f"(v[13]),"+f"(v[14]),"+f"(v[15])
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(float (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : P3P_R16(v) : : "memory");
 }
 // non-blocking probe of an mbarrier phase (the result is consumed later: its latency hides behind independent work)
 __device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {

@@ -360,10 +360,15 @@ constexpr int kTcThreads = 32 * (kEpiWarp0 + 4 * kEpiGroups);
 #ifndef P3P_REG_MMA
 #define P3P_REG_MMA 40
 #define P3P_REG_FRONT 104
-#define P3P_REG_EPI 88
+#define P3P_REG_EPI 72
 #endif
 constexpr int kRegMma = P3P_REG_MMA, kRegFront = P3P_REG_FRONT, kRegEpi = P3P_REG_EPI;  // registers per thread after setmaxnreg (launch: 80)
-static_assert(4 * kRegMma + 8 * kRegFront + 12 * kRegEpi <= 2048, "register file of the SM exceeded (65536 / 32 lanes)");
+// setmaxnreg redistributes the CTA's OWN launch allocation (24 warps x 80 registers), not the SM's spare registers: a split
+// that exceeds it leaves the last warps spinning in the allocation forever
+static_assert(4 * kRegMma + 8 * kRegFront + 12 * kRegEpi <= 24 * 80, "register pool of the launch exceeded");
+#ifndef P3P_EPI_LD
+#define P3P_EPI_LD 16  // accumulator columns per tcgen05.ld of the epilogue (16: two 16-register buffers fit 72 registers)
+#endif
 constexpr int kUnit = 8;                       // items per unit = 4 pillar pairs, consecutive canvas cells
 constexpr int kPairsPerUnit = kUnit / 2;
 constexpr int kTiles = 3;                      // 128-channel MMA tiles (C <= 384)
@@ -447,6 +452,12 @@ __device__ __forceinline__ void tmem_ld8_wait(uint32_t taddr, float (&v)[8]) {
         : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ float max16(const float (&v)[16]) {
+    float r[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) r[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    return fmax3(fmax3(r[0], r[1], r[2]), fmaxf(r[3], r[4]), v[15]);
 }
 __device__ __forceinline__ float max32(const float (&v)[32]) {
     float r[11];
@@ -892,20 +903,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
 #pragma unroll
                 for (int s = 0; s < kAccStages; ++s, ++jn) {
                     const uint32_t tph = (uint32_t)(jn >> 1) & 1u;
-                    float va[32], vb[32];
                     if (quad == 0) PTL(9 + g, jn, 0);
                     if (!ready) mbar_wait_sa(tf_sa + 8u * s, tph);
                     if (quad == 0) PTL(9 + g, jn, 1);
                     tc_fence_after();
-                    tmem_ld32_issue(taddr_o + (uint32_t)(s * kAccCols), va);
-                    tmem_ld_wait(va);
-                    tmem_ld32_issue(taddr_o + (uint32_t)(s * kAccCols + 32), vb);
-                    ready = (jn + 1 < my_pillars) ? mbar_test_sa(tf_sa + 8u * (s ^ 1), (uint32_t)((jn + 1) >> 1) & 1u) : 0u;
-                    const float r0 = max32(va);
-                    tmem_ld_wait(vb);
-                    tc_fence_before();
-                    mbar_arrive_sa(te_sa + 8u * s);
-                    my_rmax[(2 * pr + s) * 32] = fmaxf(r0, max32(vb));
+                    float rm;
+#if P3P_EPI_LD == 32
+                    {
+                        float va[32], vb[32];
+                        tmem_ld32_issue(taddr_o + (uint32_t)(s * kAccCols), va);
+                        tmem_ld_wait(va);
+                        tmem_ld32_issue(taddr_o + (uint32_t)(s * kAccCols + 32), vb);
+                        ready = (jn + 1 < my_pillars) ? mbar_test_sa(tf_sa + 8u * (s ^ 1), (uint32_t)((jn + 1) >> 1) & 1u) : 0u;
+                        const float r0 = max32(va);
+                        tmem_ld_wait(vb);
+                        tc_fence_before();
+                        mbar_arrive_sa(te_sa + 8u * s);
+                        rm = fmaxf(r0, max32(vb));
+                    }
+#else
+                    {
+                        // four loads of 16 columns through two register buffers: the arithmetic on one buffer overlaps
+                        // with the load into the other
+                        float va[16], vb[16];
+                        tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols), va);
+                        tmem_ld_wait16(va);
+                        tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 16), vb);
+                        ready = (jn + 1 < my_pillars) ? mbar_test_sa(tf_sa + 8u * (s ^ 1), (uint32_t)((jn + 1) >> 1) & 1u) : 0u;
+                        const float r0 = max16(va);
+                        tmem_ld_wait16(vb);
+                        tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 32), va);
+                        const float r1 = max16(vb);
+                        tmem_ld_wait16(va);
+                        tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 48), vb);
+                        const float r2 = max16(va);
+                        tmem_ld_wait16(vb);
+                        tc_fence_before();
+                        mbar_arrive_sa(te_sa + 8u * s);
+                        rm = fmaxf(fmax3(r0, r1, r2), max16(vb));
+                    }
+#endif
+                    my_rmax[(2 * pr + s) * 32] = rm;
                     if (quad == 0) PTL(9 + g, jn, 2);
                 }
             }

@@ -8,19 +8,20 @@
 // fixed-point mean over that set), so nothing is sorted here:
 //
 //   * a CTA takes a ticket (atomic counter) -> chunk of <= 4096 consecutive points of one tile.  Tickets, not
-//     blockIdx, order the chunks, so a CTA only ever waits for CTAs that are already running.
-//   * every lane hashes its <= 16 points (all loads in flight at once) with the reference's fp32 operation order;
-//     only the packed (key, rank) word of a point stays in a register.
-//   * each warp owns a contiguous segment of the chunk and counts it per key in a private shared-memory histogram,
-//     32 consecutive points per step: read the key's count, then one shared-memory atomic per point; same-key lanes
-//     of a step receive consecutive counts in arbitrary order.  No retry loops, no match.any.
+//     blockIdx, order the chunks, so a CTA only ever waits for CTAs that are already running.  Chunks start at
+//     multiples of 4 points of the packed xyz array: a lane moves 4 points with three aligned 16-byte loads.
+//   * every lane hashes its <= 16 points with the reference's fp32 operation order and counts them in ONE
+//     shared-memory histogram of the chunk, one atomic per point; only the packed (key, value returned by the atomic)
+//     word of a point stays in a register.
 //   * the chunk's per-key counts are published to global memory and a flag is released; the CTA acquires the flags
-//     of the earlier chunks of its tile, sums their counts per key (exclusive prefix over chunks, then over its own
-//     warps) and walks its registers again: rank = base + rank-in-segment; survivors (rank < M) re-read their xyz
-//     (L1/L2 hit) and go to slots[tile][key][rank].  Inside one step same-key lanes hold their ranks in arbitrary
-//     order, which only matters in the step where the key crosses M: that step re-ranks in lane order
-//     (match.any, about 1 % of the steps).  The kept set is therefore exactly the reference's; the order inside a
-//     pillar is not (export_kernel sorts by index for the parity surface).
+//     of the earlier chunks of its tile and sums their counts per key (pre).  Keys with pre >= M keep nothing of the
+//     chunk; keys with pre + own <= M keep everything, in slots pre + (atomic value) -- any bijection will do; the few
+//     keys that cross M inside the chunk (at most one chunk per key and tile) keep their M - pre lowest-index points,
+//     found exactly by a two-digit radix selection over the chunk-local index.  The kept set is therefore exactly the
+//     reference's whatever order the hardware serves the atomics in; the order inside a pillar is not the reference's
+//     (export_kernel sorts by index for the parity surface).
+//   * a chunk that sees every regular cell full publishes that; later chunks of the tile (multi-wave launches: dense
+//     tiles) then only handle the keys beyond the regular cells.
 //   * the last CTA of a tile to finish runs the tile's plan: keys in ascending order -> run ordinal (max_voxels
 //     cut), cell coordinates (decoded from the key; from the lowest-index point when the run holds a point on the
 //     x / y max face, i.e. under hash aliasing), x/y bound filter, final voxel order, and the canvas owner table
@@ -63,7 +64,9 @@ struct ChunkLoc {
     int c;        // chunk index inside the tile
     int nchunks;  // chunks of the tile
     int gstart;   // global index of the tile's chunk 0
-    long long p0, p1, tile_start;
+    long long p0;      // first point of the chunk's nominal range: a multiple of 4 (may lie up to 3 points before the tile)
+    long long lo, hi;  // the tile's own points: [lo, hi)
+    unsigned sat;      // the tile's saturation word as read once for the whole CTA
 };
 
 // predicated 16-bit shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic, no branches)
@@ -107,7 +110,8 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Executed by warp 0: map ticket -> (tile, local chunk).  Tiles are walked 32 at a time.
+// Executed by warp 0: map ticket -> (tile, local chunk).  Tiles are walked 32 at a time.  The chunks of a tile start at
+// its first point rounded down to a multiple of 4.
 __device__ void locate_chunk(int g, const int64_t* __restrict__ offsets, int B, int S, ChunkLoc* out) {
     const int lane = threadIdx.x & 31;
     int base = 0;
@@ -116,7 +120,8 @@ __device__ void locate_chunk(int g, const int64_t* __restrict__ offsets, int B, 
         const int t = t0 + lane;
         long long o0 = 0, o1 = 0;
         if (t < B) { o0 = offsets[t]; o1 = offsets[t + 1]; }
-        const long long n = o1 > o0 ? o1 - o0 : 0;
+        const long long a0 = o0 & ~3ll;
+        const long long n = o1 > o0 ? o1 - a0 : 0;
         const int nc = (int)((n + S - 1) / S);
         int incl = nc;
 #pragma unroll
@@ -134,9 +139,9 @@ __device__ void locate_chunk(int g, const int64_t* __restrict__ offsets, int B, 
                 out->c = g - excl;
                 out->nchunks = nc;
                 out->gstart = excl;
-                out->tile_start = o0;
-                out->p0 = o0 + (long long)(g - excl) * S;
-                out->p1 = (out->p0 + S < o1) ? out->p0 + S : o1;
+                out->p0 = a0 + (long long)(g - excl) * S;
+                out->lo = o0;
+                out->hi = o1;
             }
         }
         base += __shfl_sync(0xffffffffu, incl, 31);
@@ -267,39 +272,53 @@ __device__ void plan_tile(const GridDev& g, const WsPtrs& ws, int b, int Keff, i
     }
 }
 
-// packed per-point word: key (13 bits) | count of the key before the point in the warp segment (10 bits) << 13 |
-// position among the same-key lanes of the point's step (5 bits) << 23
-constexpr int kKeyBits = 13, kOldBits = 10;
-constexpr unsigned kCntMask = (1u << kOldBits) - 1u;
+// packed per-point word: key (13 bits) | arbitrary-order rank of the point among the chunk's points of its key (13 bits:
+// a chunk holds <= 4096 points) << 13; -1: no key (out of range, outside the tile, or irrelevant in a saturated tile)
+constexpr int kKeyBits = 13;
+constexpr unsigned kKeyMask = (1u << kKeyBits) - 1u;
 static_assert(kMaxKeys <= (1 << kKeyBits), "key field too narrow");
-static_assert(kMaxChunkPoints / kWarps <= (1 << (kOldBits - 1)), "segment count field too narrow");
+static_assert(kMaxChunkPoints == 4096, "the crossing-key selection splits a chunk-local index into two 6-bit digits");
 static_assert(kMaxChunkPoints * 8 < 65536, "8 chunk rows must add up inside 16-bit lanes");
+constexpr int kGroups = kIters / 4;        // groups of 4 consecutive points (48 bytes = 3 x 16-byte loads) per thread
+constexpr int kCrossBatch = 128;           // crossing keys resolved per selection round
+constexpr unsigned kCrossFlag = 0x8000u;   // base_s entry: the key crosses M inside this chunk; low 15 bits = crossing id
 
 // kFast: packed xyz (stride 3), no per-point hash export, hashes beyond the cells kept (the shipped configuration): the
-// per-point branches on those options are resolved at compile time.
+// per-point branches on those options are resolved at compile time and the points travel as 16-byte loads.
+//
+// Ranking.  The rest of the path consumes, per key, the SET of its min(count, M) lowest-index points.  A chunk counts its
+// points per key with one shared-memory atomic per point; the value the atomic returns orders the chunk's points of a key
+// arbitrarily.  With pre = points of the key in the earlier chunks of the tile and own = points in this chunk:
+//   pre >= M            nothing of the chunk is kept;
+//   pre + own <= M      everything is kept, and any bijection onto slots [pre, pre + own) will do: slot = pre + atomic value;
+//   otherwise           (at most one chunk per key and tile) the M - pre lowest-index points of the chunk are kept: a
+//                       two-digit radix selection over the chunk-local index (2 x 64 bins per crossing key) finds the
+//                       index threshold exactly; survivors take the slots [pre, M) in arbitrary order.
+// No step of this depends on the order in which the hardware serves same-address atomics.
 template <bool kFast>
 __global__ void __launch_bounds__(kThreads, 3)
-voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __restrict__ offsets, int B, GridDev g, int S,
-                WsPtrs ws, int32_t* __restrict__ point_hash, int need_plan, int pdl_from) {
+voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __restrict__ offsets, int B, GridDev g, int S, WsPtrs ws, int32_t* __restrict__ point_hash, int need_plan, int pdl_from) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = g.num_keys;
     const int Kp = ws.key_stride;  // K rounded up to 8: row stride of chunk_hist (16-byte rows)
-    // [kWarps][Kp] (16-byte rows): walk 1: points of the key in the warp's segment; afterwards: points of the key in the earlier warps of the CTA
-    uint16_t* hist = reinterpret_cast<uint16_t*>(smem_raw);
-    uint16_t* ctot_s = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kWarps * Kp * sizeof(uint16_t));  // [Kp] chunk totals
-    unsigned* prefix_s = reinterpret_cast<unsigned*>(ctot_s + Kp);  // [Kp] points of the key in the earlier chunks of the tile
+    uint16_t* ctot_s = reinterpret_cast<uint16_t*>(smem_raw);   // [Kp] points of the key in this chunk; last chunk: min(count, M) of the tile
+    uint16_t* base_s = ctot_s + Kp;                             // [Kp] min(pre, M), or kCrossFlag | crossing id
+    uint16_t* need_s = base_s + Kp;                             // [Kp] by crossing id: M - pre
+    uint16_t* ccnt_s = need_s + Kp;                             // [Kp] by crossing id: survivors placed so far
+    uint16_t* thr_s = ccnt_s + Kp;                              // [kCrossBatch] selected first digit, then the index threshold
+    uint16_t* rem_s = thr_s + kCrossBatch;                      // [kCrossBatch] survivors still to find inside the selected bin
+    uint16_t* bins_s = rem_s + kCrossBatch;                     // [kCrossBatch][64]
     __shared__ ChunkLoc loc;
-    __shared__ int s_ticket, s_last, s_runs[2];
+    __shared__ int s_ticket, s_last, s_runs[2], s_ncross;
     __shared__ int warp_tot[kWarps];
 
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int stride = kFast ? 3 : stride_arg;
     TL(blockIdx.x, 0);
-    if (tid == 0) s_ticket = (int)atomicAdd(ws.sync, 1u);
+    if (tid == 0) { s_ticket = (int)atomicAdd(ws.sync, 1u); s_ncross = 0; }
     {
-        uint4* h4 = reinterpret_cast<uint4*>(hist);
-        const int n16 = kWarps * Kp * (int)sizeof(uint16_t) / 16;
-        for (int i = tid; i < n16; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
+        uint4* h4 = reinterpret_cast<uint4*>(ctot_s);
+        for (int i = tid; i < Kp / 8; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     const int ticket = s_ticket;
@@ -308,122 +327,129 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
     // dependent grid launches once every CTA has triggered or exited, i.e. when no CTA of this grid is still waiting
     // for an SM that a waiting PFN CTA could occupy.
     if (ticket >= pdl_from) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (w == 0) locate_chunk(ticket, offsets, B, S, &loc);
+    unsigned* flags = ws.sync + 1;
+    unsigned* tile_done = flags + ws.max_chunks;
+    unsigned* tile_sat = tile_done + B;
+    if (tid < 32) {
+        locate_chunk(ticket, offsets, B, S, &loc);
+        __syncwarp();
+        if (lane == 0 && loc.b >= 0) loc.sat = __ldcg(tile_sat + loc.b);  // one read: the whole CTA acts on the same value
+    }
     // tiles without points have no chunk: ticket t < B writes the empty plan of tile t
     if (ticket < B && offsets[ticket + 1] <= offsets[ticket]) write_empty_tile(g, ws, ticket);
     __syncthreads();
     if (loc.b < 0) return;
     TL(blockIdx.x, 1);
 
-    unsigned* flags = ws.sync + 1;
-    unsigned* tile_done = flags + ws.max_chunks;
-    const int segS = S / kWarps;  // multiple of 32
-    const long long seg0 = loc.p0 + (long long)w * segS;
-    const int seg_n = (int)(((seg0 + segS < loc.p1) ? seg0 + segS : loc.p1) - seg0);  // points of this warp (may be <= 0)
-    uint16_t* myhist = hist + (size_t)w * Kp;
     uint8_t* edge = ws.edge + (size_t)loc.b * K;
-    const float* seg_pts = pts + seg0 * stride;
+    const int M = g.M;
+    // A chunk c0 that finds every regular cell full (pre + own >= M) publishes 0x7fffffff - c0; chunks behind it (only
+    // those: their points have higher indices than M kept ones in every regular cell) then count the keys beyond the
+    // regular cells only.  A hint: chunks that do not see it yet just do the full work.
+    const unsigned sat_word = loc.sat;
+    const bool saturated = sat_word != 0u && (int)(0x7fffffffu - sat_word) < loc.c;
 
-    // ---- hash + walk 1, software pipelined: the loads of the second half are in flight while the first half is
-    //      counted.  Walk 1 = per-warp histogram of this warp's contiguous segment, 32 consecutive points per step.
+    // ---- hash + count: chunk-local index ci = 4 * (256 * group + tid) + e; the chunk starts at a multiple of 4 points
+    //      (loc.p0; the tile's own range is [lo, hi)), so a group of 4 points is three aligned 16-byte loads --------------
     int pk[kIters];
     // bit 0: some key may lie outside the regular cells or be aliased (a point on a max face: z == z_max, y == y_max, ...)
     // bit 1: some point sits on the x / y max face (its run's coordinates are not decodable from the key)
     int hi_key = 0;
-    constexpr int kBatch = kIters / 2;
-    float px[kBatch], py[kBatch], pz[kBatch];
-    // `full` (a std::bool_constant) resolves the bounds tests of a full 512-point segment at compile time: straight-line
-    // code, loads at immediate offsets from one lane pointer (every chunk but the last of a tile).
-    const float* lane_pts = seg_pts + (size_t)lane * stride;
-    auto load_batch = [&](int j0, auto full) {
-        constexpr bool kFull = decltype(full)::value;
+    const long long lo = loc.lo, hi = loc.hi;
+    const uint32_t ctot_sa = smem_u32(ctot_s);
+    auto load_group = [&](int gi, float (&x)[4], float (&y)[4], float (&z)[4]) {
+        const long long p = loc.p0 + 4ll * (kThreads * gi + tid);
+        if (kFast && p >= lo && p + 4 <= hi) {
+            const float4* q = reinterpret_cast<const float4*>(pts + p * 3);
+            const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+            x[0] = a.x; y[0] = a.y; z[0] = a.z; x[1] = a.w; y[1] = b.x; z[1] = b.y;
+            x[2] = b.z; y[2] = b.w; z[2] = c.x; x[3] = c.y; y[3] = c.z; z[3] = c.w;
+        } else {
 #pragma unroll
-        for (int jj = 0; jj < kBatch; ++jj) {
-            const int i = (j0 + jj) * 32 + lane;
-            if (!kFull) { px[jj] = 0.f; py[jj] = 0.f; pz[jj] = 0.f; }
-            if (kFull || i < seg_n) {
-                const float* p = lane_pts + (size_t)((j0 + jj) * 32) * stride;
-                px[jj] = __ldg(p); py[jj] = __ldg(p + 1); pz[jj] = __ldg(p + 2);
+            for (int e = 0; e < 4; ++e) {
+                x[e] = y[e] = z[e] = __int_as_float(0x7fc00000);  // NaN: no key
+                if (p + e >= lo && p + e < hi) {
+                    const float* q = pts + (p + e) * stride;
+                    x[e] = __ldg(q); y[e] = __ldg(q + 1); z[e] = __ldg(q + 2);
+                }
             }
         }
     };
-    auto hash_batch = [&](int j0, auto full) {
-        constexpr bool kFull = decltype(full)::value;
-        unsigned edge_bits = 0;  // points on the x / y max face (rare: one vote per batch, flags set on a slow path)
+    {
+        unsigned edge_bits = 0;  // points on the x / y max face (rare: flags set on a slow path)
         int kmax = -1;
+        auto hash_group = [&](int gi, const float (&x)[4], const float (&y)[4], const float (&z)[4]) {
 #pragma unroll
-        for (int jj = 0; jj < kBatch; ++jj) {
-            const int j = j0 + jj, i = j * 32 + lane;
-            pk[j] = -1;
-            if (kFull || i < seg_n) {
+            for (int e = 0; e < 4; ++e) {
                 bool on_edge;
-                const int k = point_key<!kFast>(g, px[jj], py[jj], pz[jj], on_edge);  // (kFast: the launcher checked the overflow flag)
-                pk[j] = k;
-                edge_bits |= on_edge ? (1u << j) : 0u;
+                int k = point_key<!kFast>(g, x[e], y[e], z[e], on_edge);  // (kFast: the launcher checked the overflow flag)
+                if (!kFast && point_hash) {
+                    const long long p = loc.p0 + 4ll * (kThreads * gi + tid) + e;
+                    if (p >= lo && p < hi) point_hash[p] = k;
+                }
+                edge_bits |= on_edge ? (1u << (4 * gi + e)) : 0u;
                 kmax = k > kmax ? k : kmax;
-                if (!kFast && point_hash) point_hash[seg0 + i] = k;
+                if (saturated && k < g.num_cells) k = -1;
+                pk[4 * gi + e] = k;
+            }
+        };
+        // a chunk that lies inside its tile (all but the first / last of a tile) issues its twelve 16-byte loads at once
+        const bool interior = kFast && S == kMaxChunkPoints && loc.p0 >= lo && loc.p0 + S <= hi;  // (uniform)
+        if (interior) {
+            const float4* q = reinterpret_cast<const float4*>(pts + (loc.p0 + 4ll * tid) * 3);
+            float4 v[kGroups][3];
+#pragma unroll
+            for (int gi = 0; gi < kGroups; ++gi) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) v[gi][u] = __ldg(q + (size_t)gi * (kThreads * 3) + u);
+            }
+#pragma unroll
+            for (int gi = 0; gi < kGroups; ++gi) {
+                const float4 a = v[gi][0], b = v[gi][1], c = v[gi][2];
+                const float x[4] = {a.x, a.w, b.z, c.y}, y[4] = {a.y, b.x, b.w, c.z}, z[4] = {a.z, b.y, c.x, c.w};
+                hash_group(gi, x, y, z);
+            }
+        } else {
+#pragma unroll
+            for (int gi = 0; gi < kGroups; ++gi) {
+                if (4 * kThreads * gi < S) {  // (uniform)
+                    float x[4], y[4], z[4];
+                    load_group(gi, x, y, z);
+                    hash_group(gi, x, y, z);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pk[4 * gi + e] = -1;
+                }
             }
         }
         hi_key |= ((kmax >= g.num_cells) ? 1 : 0) | (edge_bits ? 3 : 0);
-        if (__any_sync(0xffffffffu, edge_bits != 0)) {
+        if (edge_bits) {
 #pragma unroll
-            for (int jj = 0; jj < kBatch; ++jj)
-                if ((edge_bits >> (j0 + jj)) & 1u) edge[pk[j0 + jj]] = 1;  // idempotent flag, read by the tile's plan
+            for (int j = 0; j < kIters; ++j)
+                if (((edge_bits >> j) & 1u) && pk[j] >= 0) edge[pk[j]] = 1;  // idempotent flag, read by the tile's plan
         }
-    };
-    const uint32_t myhist_sa = smem_u32(myhist);
-    auto count_batch = [&](int j0, auto full) {
-        constexpr bool kFull = decltype(full)::value;
-#pragma unroll
-        for (int jj = 0; jj < kBatch; ++jj) {
-            const int j = j0 + jj;
-            if (kFull || j * 32 < seg_n) {  // warp-uniform
-                const int k = pk[j];
-                const int act = k >= 0 ? 1 : 0;
-                const uint32_t sa = myhist_sa + 2u * (unsigned)(act ? k : 0);
-                // count of the key before this step, then one atomic per point: same-key lanes of the step receive
-                // consecutive counts in arbitrary order (shared-memory operations of a warp execute in program order)
-                const unsigned before = lds_u16(sa, act);
-                const unsigned old = atoms_add_u16(sa, act);
-                if (act) pk[j] = k | (int)(old << kKeyBits) | (int)((old - before) << (kKeyBits + kOldBits));
-            }
-        }
-    };
-    auto walk1 = [&](auto full) {
-        load_batch(0, full);
-        hash_batch(0, full);
-        load_batch(kBatch, full);
         TL(blockIdx.x, 2);
-        count_batch(0, full);
-        hash_batch(kBatch, full);
-        count_batch(kBatch, full);
-    };
-    const bool full_seg = (seg_n == kIters * 32);  // warp-uniform: all 16 steps of the warp hold 32 points
-    if (full_seg) walk1(std::true_type{}); else walk1(std::false_type{});
+#pragma unroll
+        for (int j = 0; j < kIters; ++j) {
+            const int k = pk[j];
+            const int act = k >= 0 ? 1 : 0;
+            const unsigned old = atoms_add_u16(ctot_sa + 2u * (unsigned)(act ? k : 0), act);
+            if (act) pk[j] = k | (int)(old << kKeyBits);
+        }
+    }
     hi_key = (__syncthreads_or(hi_key & 1) ? 1 : 0) | (__syncthreads_or(hi_key & 2) ? 2 : 0);  // (the intrinsic ORs predicates)
     TL(blockIdx.x, 3);
     if (tid < 2) s_runs[tid] = 0;
     // ---- publish this chunk's per-key counts (full rows: zeros beyond the keys in use) ------------------------------
     const int Kreg = (g.num_cells + 7) / 8 * 8 < Kp ? (g.num_cells + 7) / 8 * 8 : Kp;  // regular cells, 16-byte granular
     {
-        // 8 keys per thread: 16-byte rows, counts added inside their 16-bit lanes (a chunk holds <= 4096 points);
-        // keys nobody hashed to stay zero, so the published rows are complete
         uint4* dst = reinterpret_cast<uint4*>(ws.chunk_hist + (size_t)ticket * Kp);
-        for (int k8 = tid; k8 < Kp / 8; k8 += kThreads) {
-            uint4 acc = make_uint4(0, 0, 0, 0);
-#pragma unroll
-            for (int ww = 0; ww < kWarps; ++ww) {
-                uint4* cell = reinterpret_cast<uint4*>(hist + (size_t)ww * Kp) + k8;
-                const uint4 t = *cell;
-                *cell = acc;  // points of the keys in the earlier warps
-                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-            }
-            reinterpret_cast<uint4*>(ctot_s)[k8] = acc;
-            dst[k8] = acc;
+        for (int k8 = tid; k8 < Kp / 8; k8 += kThreads) dst[k8] = reinterpret_cast<const uint4*>(ctot_s)[k8];
+        __syncthreads();  // every row store of the CTA happens before the release below (cumulativity)
+        if (tid == 0) {
+            __threadfence();
+            st_release(flags + ticket, 1u | ((unsigned)hi_key << 1));  // bit 0: published
         }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) st_release(flags + ticket, 1u | ((unsigned)hi_key << 1));  // bit 0: published
         TL(blockIdx.x, 4);
         // wait for the earlier chunks of the tile; learn whether any of them holds keys beyond the regular cells
         int hi_before = 0;
@@ -436,14 +462,15 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
         hi_key |= (__syncthreads_or(hi_before & 1) ? 1 : 0) | (__syncthreads_or(hi_before & 2) ? 2 : 0);
     }
     TL(blockIdx.x, 5);
-    // ---- prefix over the earlier chunks: 8 keys per thread with 16-byte L2 loads, 8 rows in flight per batch -----------
-    const int M = g.M;
+    // ---- prefix over the earlier chunks: 8 keys per thread with 16-byte L2 loads, 8 rows in flight per batch; classify
+    //      every key of the chunk (dead / free / crossing) ------------------------------------------------------------
     const bool last_chunk = (loc.c == loc.nchunks - 1);
     const int Kuse = (hi_key & 1) ? Kp : Kreg;  // keys that can be non-empty in this tile so far
-    int open_keys = 0;  // keys of this chunk that still have room (base < M): if none, nothing of the chunk is kept
+    int open_keys = 0;  // keys of this chunk that still have room (pre < M): if none, nothing of the chunk is kept
+    int all_full = 1;   // every regular cell holds >= M points after this chunk
     for (int k8 = tid; k8 < Kp / 8; k8 += kThreads) {
         unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (k8 * 8 < Kuse) {
+        if (k8 * 8 < Kuse && !(saturated && k8 * 8 + 8 <= g.num_cells)) {
             const uint4* src = reinterpret_cast<const uint4*>(ws.chunk_hist + (size_t)loc.gstart * Kp) + k8;
             const size_t row = (size_t)Kp / 8;
             const uint4* rp = src;
@@ -473,16 +500,30 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
         for (int u = 0; u < 8; ++u) {
             const int k = k8 * 8 + u;
             const unsigned own = ctot_s[k];
-            prefix_s[k] = acc[u];
-            open_keys |= (own > 0 && acc[u] < (unsigned)M) ? 1 : 0;
+            unsigned pre = acc[u];
+            if (saturated && k < g.num_cells) pre = (unsigned)M;  // (the rows of saturated chunks hold no regular counts)
+            unsigned st = pre < (unsigned)M ? pre : (unsigned)M;
+            if (own > 0 && pre < (unsigned)M) {
+                open_keys = 1;
+                if (pre + own > (unsigned)M) {  // the key crosses M inside this chunk
+                    const unsigned id = (unsigned)atomicAdd(&s_ncross, 1);
+                    need_s[id] = (uint16_t)((unsigned)M - pre);
+                    ccnt_s[id] = 0;
+                    st = kCrossFlag | id;
+                }
+            }
+            base_s[k] = (uint16_t)st;
+            if (k < g.num_cells && pre + own < (unsigned)M) all_full = 0;
             if (last_chunk) {
-                const unsigned tot = acc[u] + own;
+                const unsigned tot = pre + own;
                 if (k < K) ws.totals[(size_t)loc.b * K + k] = (int)tot;
                 ctot_s[k] = (uint16_t)(tot < (unsigned)M ? tot : (unsigned)M);  // from here on: min(count, M) of the tile
             }
         }
     }
     open_keys = __syncthreads_or(open_keys);
+    all_full = __syncthreads_and(all_full);
+    if (all_full && !saturated && !last_chunk && tid == 0) atomicMax(tile_sat + loc.b, 0x7fffffffu - (unsigned)loc.c);
     TL(blockIdx.x, 6);
     // ---- the tile's last chunk knows every count: when no run can be cut, filtered or aliased, the canvas owner table
     //      follows from the keys directly and the tile needs no plan ------------------------------
@@ -522,85 +563,123 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
         }
         if (tid == 0) ws.tile_hi[loc.b] = (hi_key & 1) | (direct << 1);
     }
-    // ---- walk 2: rank = earlier chunks + earlier warps + rank in segment; scatter the survivors ---------------------
-    auto walk2 = [&](auto full) {
-        constexpr bool kFull = decltype(full)::value;
-        // pass A: ranks (registers + shared memory only); pk[j] becomes key | rank << 13 | group position << 24 (-1: no key).
-        // Same-key lanes of a step own their ranks in arbitrary order, which only matters in the one step where the key
-        // crosses M: those steps are found with ONE warp vote for the whole chunk and re-ranked in lane (= index) order.
-        const uint32_t prefix_sa = smem_u32(prefix_s);
-        constexpr int kRankBits = 11;  // provisional rank field (clamped): M + 31 < 2^11
-        unsigned cross = 0;
+    // ---- scatter: free keys take slot pre + atomic value; crossing keys are resolved below ---------------------------
+    float4* tile_slots = ws.slots + (size_t)loc.b * K * M;
+    unsigned xmask = 0;  // this thread's points that belong to crossing keys
+    if (open_keys) {
 #pragma unroll
-        for (int j = 0; j < kIters; ++j) {
-            if (kFull || j * 32 < seg_n) {  // warp-uniform
-                const int kj = pk[j] < 0 ? -1 : (pk[j] & ((1 << kKeyBits) - 1));
-                const int old = (pk[j] >> kKeyBits) & (int)kCntMask, rnd = (pk[j] >> (kKeyBits + kOldBits)) & 31;
-                const int act = kj >= 0 ? 1 : 0;
-                const unsigned pre = act ? lds_u32(prefix_sa + 4u * (unsigned)kj, act) : (unsigned)M;
-                const unsigned wbase = lds_u16(myhist_sa + 2u * (unsigned)(act ? kj : 0), act);
-                unsigned rank = pre < (unsigned)M ? pre + wbase + (unsigned)old : (unsigned)M;
-                if ((rank >= (unsigned)M) && (rank < (unsigned)(M + rnd))) cross |= 1u << j;
-                rank = rank < (1u << kRankBits) - 1u ? rank : (1u << kRankBits) - 1u;
-                pk[j] = act ? (kj | (int)(rank << kKeyBits) | (rnd << (kKeyBits + kRankBits))) : -1;
-            } else {
-                pk[j] = -1;
+        for (int gi = 0; gi < kGroups; ++gi) {
+            unsigned keep = 0;
+            int slot[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = 4 * gi + e;
+                slot[e] = -1;
+                if (pk[j] >= 0) {
+                    const unsigned st = base_s[(unsigned)pk[j] & kKeyMask];
+                    if (st & kCrossFlag) xmask |= 1u << j;
+                    else if (st < (unsigned)M) { slot[e] = (int)(st + ((unsigned)pk[j] >> kKeyBits)); keep |= 1u << e; }
+                }
             }
-        }
-        cross = __reduce_or_sync(0xffffffffu, cross);
-        if (cross) {  // warp-uniform; about 1 % of the steps are flagged
+            if (keep) {
+                float x[4], y[4], z[4];
+                load_group(gi, x, y, z);  // (L1 / L2 hits)
 #pragma unroll
-            for (int j = 0; j < kIters; ++j) {
-                if (cross & (1u << j)) {
-                    const int kj = pk[j] < 0 ? -1 : (pk[j] & ((1 << kKeyBits) - 1));
-                    unsigned rank = (unsigned)(pk[j] >> kKeyBits) & ((1u << kRankBits) - 1u);
-                    const unsigned rnd = (unsigned)(pk[j] >> (kKeyBits + kRankBits)) & 31u;
-                    const unsigned m = __match_any_sync(0xffffffffu, kj);
-                    // lanes of a run whose first count lies below M (the others keep a rank >= M)
-                    if (kj >= 0 && rank - rnd < (unsigned)M) {
-                        rank = rank - rnd + (unsigned)__popc(m & ((1u << lane) - 1u));
-                        pk[j] = kj | (int)(rank << kKeyBits);
+                for (int e = 0; e < 4; ++e) {
+                    if (slot[e] >= 0) {
+                        const int ci = 4 * (kThreads * gi + tid) + e;
+                        tile_slots[(size_t)((unsigned)pk[4 * gi + e] & kKeyMask) * M + slot[e]] =
+                            make_float4(x[e], y[e], z[e], __int_as_float((int)(loc.p0 + ci - lo)));
                     }
                 }
             }
         }
-        TL(blockIdx.x, 7);
-        // pass B: survivors re-read their xyz (L1 / L2 hits), all loads of a batch in flight before the first store
-        float4* tile_slots = ws.slots + (size_t)loc.b * K * M;
+    }
+    TL(blockIdx.x, 7);
+    // ---- crossing keys: the need = M - pre lowest chunk-local indices survive.  Two-digit radix selection, kCrossBatch
+    //      keys per round: digit 1 = ci >> 6, digit 2 = ci & 63 (indices are unique, so the second histogram is 0 / 1) -----
+    const int ncross = s_ncross;  // (written before the barriers above)
+    for (int c0 = 0; c0 < ncross; c0 += kCrossBatch) {
+        const int nb = ncross - c0 < kCrossBatch ? ncross - c0 : kCrossBatch;
+        uint4* b4 = reinterpret_cast<uint4*>(bins_s);
+        for (int i = tid; i < kCrossBatch * 64 / 8; i += kThreads) b4[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        const uint32_t bins_sa = smem_u32(bins_s);
+        auto my_id = [&](int j) -> int {  // crossing id of point j relative to this batch, or -1
+            if (!((xmask >> j) & 1u)) return -1;
+            const int id = (int)(base_s[(unsigned)pk[j] & kKeyMask] & (kCrossFlag - 1u)) - c0;
+            return (id >= 0 && id < nb) ? id : -1;
+        };
+        auto ci_of = [&](int j) -> int { return 4 * (kThreads * (j >> 2) + tid) + (j & 3); };
+        if (xmask) {
 #pragma unroll
-        for (int j0 = 0; j0 < kIters; j0 += kBatch) {
-#pragma unroll
-            for (int jj = 0; jj < kBatch; ++jj) {
-                // survivors: a key and a (provisional or re-ranked) rank below M
-                if (pk[j0 + jj] >= 0 && (((unsigned)pk[j0 + jj] >> kKeyBits) & ((1u << kRankBits) - 1u)) >= (unsigned)M) pk[j0 + jj] = -1;
-                if (pk[j0 + jj] >= 0) {
-                    const float* p = lane_pts + (size_t)((j0 + jj) * 32) * stride;
-                    px[jj] = __ldg(p); py[jj] = __ldg(p + 1); pz[jj] = __ldg(p + 2);
-                }
+            for (int j = 0; j < kIters; ++j) {
+                const int id = my_id(j);
+                if (id >= 0) atoms_add_u16(bins_sa + 2u * (unsigned)(id * 64 + (ci_of(j) >> 6)), 1);
             }
+        }
+        __syncthreads();
+        if (tid < nb) {  // first digit: the bin in which the cumulative count reaches `need`
+            const unsigned need = need_s[c0 + tid];
+            unsigned cum = 0;
+            int b = 0;
+            for (; b < 63; ++b) {
+                const unsigned v = bins_s[tid * 64 + b];
+                if (cum + v >= need) break;
+                cum += v;
+            }
+            thr_s[tid] = (uint16_t)b;
+            rem_s[tid] = (uint16_t)(need - cum);
+        }
+        __syncthreads();
+        for (int i = tid; i < kCrossBatch * 64 / 8; i += kThreads) b4[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        if (xmask) {
 #pragma unroll
-            for (int jj = 0; jj < kBatch; ++jj) {
-                const int j = j0 + jj, i = j * 32 + lane;
-                if (pk[j] >= 0) {
-                    const int kj = pk[j] & ((1 << kKeyBits) - 1), rank = (pk[j] >> kKeyBits) & ((1 << kRankBits) - 1);
-                    tile_slots[(size_t)kj * M + rank] =
-                        make_float4(px[jj], py[jj], pz[jj], __int_as_float((int)(seg0 + i - loc.tile_start)));
+            for (int j = 0; j < kIters; ++j) {
+                const int id = my_id(j);
+                if (id >= 0 && (ci_of(j) >> 6) == (int)thr_s[id]) bins_s[id * 64 + (ci_of(j) & 63)] = 1;
+            }
+        }
+        __syncthreads();
+        if (tid < nb) {  // second digit: the rem-th occupied position of the selected bin
+            unsigned rem = rem_s[tid];
+            int t = 0;
+            for (; t < 63; ++t) {
+                rem -= bins_s[tid * 64 + t];
+                if (rem == 0) break;
+            }
+            thr_s[tid] = (uint16_t)(thr_s[tid] * 64 + t);  // survivors: ci <= this threshold
+        }
+        __syncthreads();
+        if (xmask) {
+            const uint32_t ccnt_sa = smem_u32(ccnt_s);
+#pragma unroll
+            for (int j = 0; j < kIters; ++j) {
+                const int id = my_id(j);
+                if (id >= 0 && ci_of(j) <= (int)thr_s[id]) {
+                    const unsigned r = atoms_add_u16(ccnt_sa + 2u * (unsigned)(c0 + id), 1);
+                    const unsigned pre = (unsigned)M - need_s[c0 + id];
+                    const long long p = loc.p0 + ci_of(j);
+                    const float* q = pts + p * stride;
+                    tile_slots[(size_t)((unsigned)pk[j] & kKeyMask) * M + pre + r] =
+                        make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __int_as_float((int)(p - lo)));
                 }
             }
         }
-    };
-    if (open_keys) {
-        if (full_seg) walk2(std::true_type{}); else walk2(std::false_type{});
+        __syncthreads();
     }
     // ---- the last CTA of the tile to get here plans the tile ------------------------------------------------------------
     TL(blockIdx.x, 8);
-    __threadfence();
-    __syncthreads();
+    __syncthreads();  // every slot / table store of the CTA happens before the fence of thread 0 (cumulativity)
     TL(blockIdx.x, 9);
-    if (tid == 0) s_last = (atomicAdd(tile_done + loc.b, 1u) == (unsigned)(loc.nchunks - 1)) ? 1 : 0;
+    if (tid == 0) {
+        __threadfence();
+        s_last = (atomicAdd(tile_done + loc.b, 1u) == (unsigned)(loc.nchunks - 1)) ? 1 : 0;
+        __threadfence();
+    }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
     TL(blockIdx.x, 10);
     const int tile_hi = __ldcg(ws.tile_hi + loc.b);
     if (tile_hi & 2) return;  // owner table already written by the tile's last chunk
@@ -655,23 +734,22 @@ export_kernel(GridDev g, int B, WsPtrs ws, p3p_voxel_outputs out) {
 
 }  // namespace
 
-static size_t voxelize_smem_bytes(const GridDev& g) {
+size_t voxelize_smem_bytes(const GridDev& g) {
     const size_t kp = ((size_t)g.num_keys + 7) / 8 * 8;
-    const size_t hist = (size_t)kWarps * kp * sizeof(uint16_t) + kp * (sizeof(uint16_t) + sizeof(unsigned));
+    // chunk counts, bases, crossing needs / counters (uint16 [kp] each), selection scratch
+    const size_t rank = 4 * kp * sizeof(uint16_t) + 2 * kCrossBatch * sizeof(uint16_t) + (size_t)kCrossBatch * 64 * sizeof(uint16_t);
     const size_t plan = (size_t)(4 * g.num_keys + g.ny * g.nx) * sizeof(int);
-    return ((hist > plan ? hist : plan) + 15) / 16 * 16;
+    return ((rank > plan ? rank : plan) + 15) / 16 * 16;
 }
 
 int launch_voxelize(const float* pts, int stride, const int64_t* offsets, int B, int64_t total, const GridDev& g,
                     const WsLayout& l, const WsPtrs& ws, int32_t* point_hash, int need_plan, cudaStream_t st) {
     (void)total;
     const size_t smem = voxelize_smem_bytes(g);
-    static bool attr_done = false;
-    if (!attr_done) {
-        P3P_CUDA_CHECK(cudaFuncSetAttribute(voxelize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        P3P_CUDA_CHECK(cudaFuncSetAttribute(voxelize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    if (smem > kVoxelizeMaxSmem) return fail(P3P_ERR_UNSUPPORTED, "voxel grid needs %zu bytes of shared memory per CTA (limit %zu)", smem, kVoxelizeMaxSmem);
+    // (the attribute belongs to the current device's context: set per launch, it is cheap)
+    P3P_CUDA_CHECK(cudaFuncSetAttribute(voxelize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVoxelizeMaxSmem));
+    P3P_CUDA_CHECK(cudaFuncSetAttribute(voxelize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVoxelizeMaxSmem));
     // ticket counter, chunk flags and per-tile completion counters start at zero for every call
     P3P_CUDA_CHECK(cudaMemsetAsync(ws.sync, 0, l.sync_bytes, st));
     const int pdl_from = l.max_chunks - device_sm_count();  // tickets of the last (partial) wave

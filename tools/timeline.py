@@ -37,7 +37,7 @@ t = np.frombuffer(buf, dtype=np.uint64).reshape(n, 16).astype(np.int64)
 used = t[:, 0] > 0
 t = t[used]
 t0 = t[:, 0].min()
-names = ["start", "located", "hashed", "walk1", "published", "acquired", "prefix", "ranked", "walk2", "fenced", "plan0", "plan1"]
+names = ["start", "located", "hashed", "counted", "published", "acquired", "classified", "scattered", "crossing", "synced", "plan0", "plan1"]
 print(f"{used.sum()} CTAs; times in us relative to the first CTA start")
 for i, nm in enumerate(names):
     col = t[:, i]
