@@ -64,7 +64,7 @@ struct ChunkLoc {
     int c;        // chunk index inside the tile
     int nchunks;  // chunks of the tile
     int gstart;   // global index of the tile's chunk 0
-    long long p0;      // first point of the chunk's nominal range: a multiple of 4 (may lie up to 3 points before the tile)
+    long long p0;      // first point of the chunk's nominal range: 16-byte aligned in the packed array (may lie up to 3 points before the tile)
     long long lo, hi;  // the tile's own points: [lo, hi)
     unsigned sat;      // the tile's saturation word as read once for the whole CTA
 };
@@ -111,8 +111,9 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 }
 
 // Executed by warp 0: map ticket -> (tile, local chunk).  Tiles are walked 32 at a time.  The chunks of a tile start at
-// its first point rounded down to a multiple of 4.
-__device__ void locate_chunk(int g, const int64_t* __restrict__ offsets, int B, int S, ChunkLoc* out) {
+// its first point rounded down to an index = phase (mod 4), the indices at which the packed xyz array is 16-byte aligned
+// (address = base + 12 * index; phase = (base / 4) mod 4).
+__device__ void locate_chunk(int g, const int64_t* __restrict__ offsets, int B, int S, int phase, ChunkLoc* out) {
     const int lane = threadIdx.x & 31;
     int base = 0;
     bool found = false;
@@ -120,7 +121,7 @@ __device__ void locate_chunk(int g, const int64_t* __restrict__ offsets, int B, 
         const int t = t0 + lane;
         long long o0 = 0, o1 = 0;
         if (t < B) { o0 = offsets[t]; o1 = offsets[t + 1]; }
-        const long long a0 = o0 & ~3ll;
+        const long long a0 = o0 - ((o0 - phase) & 3ll);  // largest index <= o0 that is = phase (mod 4)
         const long long n = o1 > o0 ? o1 - a0 : 0;
         const int nc = (int)((n + S - 1) / S);
         int incl = nc;
@@ -277,10 +278,11 @@ __device__ void plan_tile(const GridDev& g, const WsPtrs& ws, int b, int Keff, i
 constexpr int kKeyBits = 13;
 constexpr unsigned kKeyMask = (1u << kKeyBits) - 1u;
 static_assert(kMaxKeys <= (1 << kKeyBits), "key field too narrow");
-static_assert(kMaxChunkPoints == 4096, "the crossing-key selection splits a chunk-local index into two 6-bit digits");
 static_assert(kMaxChunkPoints * 8 < 65536, "8 chunk rows must add up inside 16-bit lanes");
 constexpr int kGroups = kIters / 4;        // groups of 4 consecutive points (48 bytes = 3 x 16-byte loads) per thread
-constexpr int kCrossBatch = 128;           // crossing keys resolved per selection round
+constexpr int kCrossBatch = 256;           // crossing keys resolved per round
+constexpr int kCells = kGroups * kWarps;   // the chunk-local order is (group, warp, lane, e): 32 cells (group, warp) of 128 consecutive points
+static_assert(kMaxChunkPoints / kCells <= 255, "points of a cell must fit the 8-bit fields of the boundary word");
 constexpr unsigned kCrossFlag = 0x8000u;   // base_s entry: the key crosses M inside this chunk; low 15 bits = crossing id
 
 // kFast: packed xyz (stride 3), no per-point hash export, hashes beyond the cells kept (the shipped configuration): the
@@ -304,10 +306,8 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
     uint16_t* ctot_s = reinterpret_cast<uint16_t*>(smem_raw);   // [Kp] points of the key in this chunk; last chunk: min(count, M) of the tile
     uint16_t* base_s = ctot_s + Kp;                             // [Kp] min(pre, M), or kCrossFlag | crossing id
     uint16_t* need_s = base_s + Kp;                             // [Kp] by crossing id: M - pre
-    uint16_t* ccnt_s = need_s + Kp;                             // [Kp] by crossing id: survivors placed so far
-    uint16_t* thr_s = ccnt_s + Kp;                              // [kCrossBatch] selected first digit, then the index threshold
-    uint16_t* rem_s = thr_s + kCrossBatch;                      // [kCrossBatch] survivors still to find inside the selected bin
-    uint16_t* bins_s = rem_s + kCrossBatch;                     // [kCrossBatch][64]
+    unsigned* bnd_s = reinterpret_cast<unsigned*>(need_s + Kp); // [kCrossBatch] boundary cell | survivors in it << 8 | its count << 16
+    uint16_t* cell_s = reinterpret_cast<uint16_t*>(bnd_s + kCrossBatch);  // [kCells][kCrossBatch] per-cell counts, then their exclusive prefix
     __shared__ ChunkLoc loc;
     __shared__ int s_ticket, s_last, s_runs[2], s_ncross;
     __shared__ int warp_tot[kWarps];
@@ -331,7 +331,7 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
     unsigned* tile_done = flags + ws.max_chunks;
     unsigned* tile_sat = tile_done + B;
     if (tid < 32) {
-        locate_chunk(ticket, offsets, B, S, &loc);
+        locate_chunk(ticket, offsets, B, S, kFast ? (int)((reinterpret_cast<uintptr_t>(pts) >> 2) & 3u) : 0, &loc);
         __syncwarp();
         if (lane == 0 && loc.b >= 0) loc.sat = __ldcg(tile_sat + loc.b);  // one read: the whole CTA acts on the same value
     }
@@ -357,6 +357,8 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
     int hi_key = 0;
     const long long lo = loc.lo, hi = loc.hi;
     const uint32_t ctot_sa = smem_u32(ctot_s);
+    // a chunk that lies inside its tile (all but the first / last of a tile) issues its twelve 16-byte loads at once
+    const bool interior = kFast && S == kMaxChunkPoints && loc.p0 >= lo && loc.p0 + S <= hi;  // (uniform)
     auto load_group = [&](int gi, float (&x)[4], float (&y)[4], float (&z)[4]) {
         const long long p = loc.p0 + 4ll * (kThreads * gi + tid);
         if (kFast && p >= lo && p + 4 <= hi) {
@@ -393,8 +395,6 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
                 pk[4 * gi + e] = k;
             }
         };
-        // a chunk that lies inside its tile (all but the first / last of a tile) issues its twelve 16-byte loads at once
-        const bool interior = kFast && S == kMaxChunkPoints && loc.p0 >= lo && loc.p0 + S <= hi;  // (uniform)
         if (interior) {
             const float4* q = reinterpret_cast<const float4*>(pts + (loc.p0 + 4ll * tid) * 3);
             float4 v[kGroups][3];
@@ -508,7 +508,6 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
                 if (pre + own > (unsigned)M) {  // the key crosses M inside this chunk
                     const unsigned id = (unsigned)atomicAdd(&s_ncross, 1);
                     need_s[id] = (uint16_t)((unsigned)M - pre);
-                    ccnt_s[id] = 0;
                     st = kCrossFlag | id;
                 }
             }
@@ -563,114 +562,185 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
         }
         if (tid == 0) ws.tile_hi[loc.b] = (hi_key & 1) | (direct << 1);
     }
-    // ---- scatter: free keys take slot pre + atomic value; crossing keys are resolved below ---------------------------
+    // ---- slots: free keys take slot pre + atomic value; crossing keys are resolved below; then one store pass ---------
+    // pk[j] becomes key | slot << 13 for a survivor, -1 otherwise
     float4* tile_slots = ws.slots + (size_t)loc.b * K * M;
     unsigned xmask = 0;  // this thread's points that belong to crossing keys
+    const int w = tid >> 5;
     if (open_keys) {
 #pragma unroll
-        for (int gi = 0; gi < kGroups; ++gi) {
-            unsigned keep = 0;
-            int slot[4];
+        for (int j = 0; j < kIters; ++j) {
+            if (pk[j] >= 0) {
+                const unsigned key = (unsigned)pk[j] & kKeyMask;
+                const unsigned st = base_s[key];
+                if (st & kCrossFlag) xmask |= 1u << j;
+                else if (st < (unsigned)M) pk[j] = (int)(key | ((st + ((unsigned)pk[j] >> kKeyBits)) << kKeyBits));
+                else pk[j] = -1;
+            }
+        }
+    } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = 4 * gi + e;
-                slot[e] = -1;
-                if (pk[j] >= 0) {
-                    const unsigned st = base_s[(unsigned)pk[j] & kKeyMask];
-                    if (st & kCrossFlag) xmask |= 1u << j;
-                    else if (st < (unsigned)M) { slot[e] = (int)(st + ((unsigned)pk[j] >> kKeyBits)); keep |= 1u << e; }
+        for (int j = 0; j < kIters; ++j) pk[j] = -1;
+    }
+    TL(blockIdx.x, 7);
+    // ---- crossing keys: the need = M - pre lowest chunk-local indices survive.  The chunk-local order is (group, warp,
+    //      lane, e): 32 cells (group, warp) of 128 points.  Per crossing key: count per cell (one atomic per point, its
+    //      return value orders the key's points of a cell arbitrarily), exclusive prefix over the cells, the cell in which
+    //      the prefix crosses `need`: cells before it survive whole (slot = pre + prefix + atomic value), cells behind it
+    //      not at all, and inside the boundary cell the warp that owns it ranks the key's points in (lane, e) order with
+    //      ballots.  kCrossBatch keys per round.
+    const int ncross = s_ncross;  // (written before the barriers above)
+    for (int c0 = 0; c0 < ncross; c0 += kCrossBatch) {
+        const int nb = ncross - c0 < kCrossBatch ? ncross - c0 : kCrossBatch;
+        {
+            uint4* c4 = reinterpret_cast<uint4*>(cell_s);
+            for (int i = tid; i < kCells * kCrossBatch / 8; i += kThreads) c4[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        const uint32_t cell_sa = smem_u32(cell_s);
+        unsigned bmask = 0;  // this thread's crossing points of the batch
+        if (xmask) {
+#pragma unroll
+            for (int j = 0; j < kIters; ++j) {
+                if ((xmask >> j) & 1u) {
+                    const unsigned key = (unsigned)pk[j] & kKeyMask;
+                    const int id = (int)(base_s[key] & (kCrossFlag - 1u)) - c0;
+                    if (id >= 0 && id < nb) {
+                        bmask |= 1u << j;
+                        const unsigned cell = (unsigned)((j >> 2) * kWarps + w);
+                        const unsigned local = atoms_add_u16(cell_sa + 2u * (cell * kCrossBatch + (unsigned)id), 1);
+                        pk[j] = (int)(key | (local << kKeyBits));
+                    }
                 }
             }
-            if (keep) {
-                float x[4], y[4], z[4];
-                load_group(gi, x, y, z);  // (L1 / L2 hits)
+        }
+        __syncthreads();
+        if (tid < nb) {  // exclusive prefix over the 32 cells (conflict-free: ids are the fast index), boundary cell
+            const unsigned need = need_s[c0 + tid];
+            unsigned P = 0, bnd = 0;
+            bool found = false;
+#pragma unroll 8
+            for (int c = 0; c < kCells; ++c) {
+                const unsigned v = cell_s[c * kCrossBatch + tid];
+                cell_s[c * kCrossBatch + tid] = (uint16_t)P;
+                if (!found && P + v >= need) { found = true; bnd = (unsigned)c | ((need - P) << 8) | (v << 16); }
+                P += v;
+            }
+            bnd_s[tid] = bnd;  // cell | survivors inside it << 8 | its points of the key << 16
+        }
+        __syncthreads();
+        if (__any_sync(0xffffffffu, bmask != 0)) {
+#pragma unroll
+            for (int gi = 0; gi < kGroups; ++gi) {
+                const unsigned cell = (unsigned)(gi * kWarps + w);
+                unsigned flag = 0;  // per e: boundary-cell point whose fate depends on the (lane, e) order
+                int keyv[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    if (slot[e] >= 0) {
-                        const int ci = 4 * (kThreads * gi + tid) + e;
-                        tile_slots[(size_t)((unsigned)pk[4 * gi + e] & kKeyMask) * M + slot[e]] =
-                            make_float4(x[e], y[e], z[e], __int_as_float((int)(loc.p0 + ci - lo)));
+                    const int j = 4 * gi + e;
+                    keyv[e] = -1;
+                    if ((bmask >> j) & 1u) {
+                        const unsigned key = (unsigned)pk[j] & kKeyMask, local = (unsigned)pk[j] >> kKeyBits;
+                        const int id = (int)(base_s[key] & (kCrossFlag - 1u)) - c0;
+                        const unsigned bnd = bnd_s[id], bc = bnd & 0xFFu, rem = (bnd >> 8) & 0xFFu, cnt = bnd >> 16;
+                        const unsigned pre = (unsigned)M - need_s[c0 + id];
+                        const unsigned P = cell_s[cell * kCrossBatch + (unsigned)id];
+                        if (cell < bc || (cell == bc && rem == cnt)) pk[j] = (int)(key | ((pre + P + local) << kKeyBits));
+                        else if (cell > bc) pk[j] = -1;
+                        else { flag |= 1u << e; keyv[e] = (int)key; }
+                    }
+                }
+                unsigned pending = __ballot_sync(0xffffffffu, flag != 0);
+                while (pending) {  // one round per distinct boundary key of this cell (warp-uniform loop)
+                    const int leader = __ffs(pending) - 1;
+                    const int mine = (flag & 1u) ? keyv[0] : ((flag & 2u) ? keyv[1] : ((flag & 4u) ? keyv[2] : keyv[3]));
+                    const int kk = __shfl_sync(0xffffffffu, mine, leader);
+                    unsigned b[4], m = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool hit = ((flag >> e) & 1u) && keyv[e] == kk;
+                        m |= hit ? (1u << e) : 0u;
+                        b[e] = __ballot_sync(0xffffffffu, hit);
+                    }
+                    if (m) {
+                        const int id = (int)(base_s[kk] & (kCrossFlag - 1u)) - c0;
+                        const unsigned rem = (bnd_s[id] >> 8) & 0xFFu;
+                        const unsigned pre = (unsigned)M - need_s[c0 + id];
+                        const unsigned P = cell_s[cell * kCrossBatch + (unsigned)id];
+                        const unsigned lt = (1u << lane) - 1u;
+                        unsigned below = (unsigned)(__popc(b[0] & lt) + __popc(b[1] & lt) + __popc(b[2] & lt) + __popc(b[3] & lt));
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if ((m >> e) & 1u) {
+                                pk[4 * gi + e] = below < rem ? (int)((unsigned)kk | ((pre + P + below) << kKeyBits)) : -1;
+                                ++below;
+                            }
+                        }
+                        flag &= ~m;
+                    }
+                    pending = __ballot_sync(0xffffffffu, flag != 0);
+                }
+            }
+        }
+        xmask &= ~bmask;
+        __syncthreads();
+    }
+    TL(blockIdx.x, 8);
+    // ---- store pass: survivors re-read their xyz (L1 / L2 hits; all loads of the chunk in flight at once) ----------------
+    {
+        unsigned live = 0;  // groups with a survivor
+#pragma unroll
+        for (int j = 0; j < kIters; ++j) live |= (pk[j] >= 0) ? (1u << (j >> 2)) : 0u;
+        if (interior) {
+            const float4* q = reinterpret_cast<const float4*>(pts + (loc.p0 + 4ll * tid) * 3);
+#pragma unroll
+            for (int h = 0; h < kGroups; h += 2) {  // two groups (six loads) in flight at a time: register budget
+                float4 v[2][3];
+#pragma unroll
+                for (int g2 = 0; g2 < 2; ++g2) {
+                    if ((live >> (h + g2)) & 1u) {
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) v[g2][u] = __ldg(q + (size_t)(h + g2) * (kThreads * 3) + u);
+                    }
+                }
+#pragma unroll
+                for (int g2 = 0; g2 < 2; ++g2) {
+                    const int gi = h + g2;
+                    if ((live >> gi) & 1u) {
+                        const float4 a = v[g2][0], b = v[g2][1], c = v[g2][2];
+                        const float x[4] = {a.x, a.w, b.z, c.y}, y[4] = {a.y, b.x, b.w, c.z}, z[4] = {a.z, b.y, c.x, c.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = 4 * gi + e;
+                            if (pk[j] >= 0) {
+                                const int ci = 4 * (kThreads * gi + tid) + e;
+                                tile_slots[(size_t)((unsigned)pk[j] & kKeyMask) * M + ((unsigned)pk[j] >> kKeyBits)] =
+                                    make_float4(x[e], y[e], z[e], __int_as_float((int)(loc.p0 + ci - lo)));
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int gi = 0; gi < kGroups; ++gi) {
+                if ((live >> gi) & 1u) {
+                    float x[4], y[4], z[4];
+                    load_group(gi, x, y, z);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = 4 * gi + e;
+                        if (pk[j] >= 0) {
+                            const int ci = 4 * (kThreads * gi + tid) + e;
+                            tile_slots[(size_t)((unsigned)pk[j] & kKeyMask) * M + ((unsigned)pk[j] >> kKeyBits)] =
+                                make_float4(x[e], y[e], z[e], __int_as_float((int)(loc.p0 + ci - lo)));
+                        }
                     }
                 }
             }
         }
     }
-    TL(blockIdx.x, 7);
-    // ---- crossing keys: the need = M - pre lowest chunk-local indices survive.  Two-digit radix selection, kCrossBatch
-    //      keys per round: digit 1 = ci >> 6, digit 2 = ci & 63 (indices are unique, so the second histogram is 0 / 1) -----
-    const int ncross = s_ncross;  // (written before the barriers above)
-    for (int c0 = 0; c0 < ncross; c0 += kCrossBatch) {
-        const int nb = ncross - c0 < kCrossBatch ? ncross - c0 : kCrossBatch;
-        uint4* b4 = reinterpret_cast<uint4*>(bins_s);
-        for (int i = tid; i < kCrossBatch * 64 / 8; i += kThreads) b4[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        const uint32_t bins_sa = smem_u32(bins_s);
-        auto my_id = [&](int j) -> int {  // crossing id of point j relative to this batch, or -1
-            if (!((xmask >> j) & 1u)) return -1;
-            const int id = (int)(base_s[(unsigned)pk[j] & kKeyMask] & (kCrossFlag - 1u)) - c0;
-            return (id >= 0 && id < nb) ? id : -1;
-        };
-        auto ci_of = [&](int j) -> int { return 4 * (kThreads * (j >> 2) + tid) + (j & 3); };
-        if (xmask) {
-#pragma unroll
-            for (int j = 0; j < kIters; ++j) {
-                const int id = my_id(j);
-                if (id >= 0) atoms_add_u16(bins_sa + 2u * (unsigned)(id * 64 + (ci_of(j) >> 6)), 1);
-            }
-        }
-        __syncthreads();
-        if (tid < nb) {  // first digit: the bin in which the cumulative count reaches `need`
-            const unsigned need = need_s[c0 + tid];
-            unsigned cum = 0;
-            int b = 0;
-            for (; b < 63; ++b) {
-                const unsigned v = bins_s[tid * 64 + b];
-                if (cum + v >= need) break;
-                cum += v;
-            }
-            thr_s[tid] = (uint16_t)b;
-            rem_s[tid] = (uint16_t)(need - cum);
-        }
-        __syncthreads();
-        for (int i = tid; i < kCrossBatch * 64 / 8; i += kThreads) b4[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        if (xmask) {
-#pragma unroll
-            for (int j = 0; j < kIters; ++j) {
-                const int id = my_id(j);
-                if (id >= 0 && (ci_of(j) >> 6) == (int)thr_s[id]) bins_s[id * 64 + (ci_of(j) & 63)] = 1;
-            }
-        }
-        __syncthreads();
-        if (tid < nb) {  // second digit: the rem-th occupied position of the selected bin
-            unsigned rem = rem_s[tid];
-            int t = 0;
-            for (; t < 63; ++t) {
-                rem -= bins_s[tid * 64 + t];
-                if (rem == 0) break;
-            }
-            thr_s[tid] = (uint16_t)(thr_s[tid] * 64 + t);  // survivors: ci <= this threshold
-        }
-        __syncthreads();
-        if (xmask) {
-            const uint32_t ccnt_sa = smem_u32(ccnt_s);
-#pragma unroll
-            for (int j = 0; j < kIters; ++j) {
-                const int id = my_id(j);
-                if (id >= 0 && ci_of(j) <= (int)thr_s[id]) {
-                    const unsigned r = atoms_add_u16(ccnt_sa + 2u * (unsigned)(c0 + id), 1);
-                    const unsigned pre = (unsigned)M - need_s[c0 + id];
-                    const long long p = loc.p0 + ci_of(j);
-                    const float* q = pts + p * stride;
-                    tile_slots[(size_t)((unsigned)pk[j] & kKeyMask) * M + pre + r] =
-                        make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __int_as_float((int)(p - lo)));
-                }
-            }
-        }
-        __syncthreads();
-    }
     // ---- the last CTA of the tile to get here plans the tile ------------------------------------------------------------
-    TL(blockIdx.x, 8);
     __syncthreads();  // every slot / table store of the CTA happens before the fence of thread 0 (cumulativity)
     TL(blockIdx.x, 9);
     if (tid == 0) {
@@ -737,7 +807,7 @@ export_kernel(GridDev g, int B, WsPtrs ws, p3p_voxel_outputs out) {
 size_t voxelize_smem_bytes(const GridDev& g) {
     const size_t kp = ((size_t)g.num_keys + 7) / 8 * 8;
     // chunk counts, bases, crossing needs / counters (uint16 [kp] each), selection scratch
-    const size_t rank = 4 * kp * sizeof(uint16_t) + 2 * kCrossBatch * sizeof(uint16_t) + (size_t)kCrossBatch * 64 * sizeof(uint16_t);
+    const size_t rank = 3 * kp * sizeof(uint16_t) + kCrossBatch * sizeof(unsigned) + (size_t)kCells * kCrossBatch * sizeof(uint16_t);
     const size_t plan = (size_t)(4 * g.num_keys + g.ny * g.nx) * sizeof(int);
     return ((rank > plan ? rank : plan) + 15) / 16 * 16;
 }
