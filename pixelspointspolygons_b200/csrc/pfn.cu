@@ -888,68 +888,64 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         // the NEXT pillar's barrier is issued before the arithmetic on the current one, so that in the steady state (the
         // issuer runs ahead) no wait is exposed.
         uint32_t ready = 0;
-        float* my_rmax = sRmax + (warp - kEpiWarp0) * (kUnit * 32) + lane;  // [kUnit][32 lanes] strip of this warp
+        bool inflight = false;  // the first 16 columns of the pillar in work are already on their way into va
+        float va[16], vb[16];
+        const uint32_t rmax_sa = opaque(smem_u32(sRmax + (warp - kEpiWarp0) * (kUnit * 32) + lane));  // [kUnit][32 lanes] strip of this warp
+        const uint32_t valid_sa = opaque(smem_u32(sValid));
         const uint32_t taddr_o = opaque(taddr);
+        // rows layout: this thread's channel of the unit's first cell; advanced by one pointer addition per unit
+        float* rows_dst = static_cast<float*>(a.out) + (int64_t)blockIdx.x * kUnit * C + c;
+        const int64_t rows_step = (int64_t)gridDim.x * kUnit * C;
         for (int j = 0; j < (g < MT ? my_units : 0); ++j) {
             const int ub = wu.b, ur = wu.r;  // tile / position of the unit's first item
             const int item0 = unit_item0;
             wu.step();
             unit_item0 += (int)gridDim.x * kUnit;
             // ---- the unit's 8 pillars: max over each pillar's 64 accumulator columns ---------------------------------
-            // (a rolled loop over the pairs: the 32-register blocks of the two loads keep one assignment; the pillar
-            // maxima wait for the unit's W1b' hmax term in a per-warp shared-memory strip, not in registers)
+            // (a rolled loop over the pairs: the register blocks of the loads keep one assignment; the pillar maxima wait
+            // for the unit's W1b' hmax term in a per-warp shared-memory strip, not in registers).  The loads form one
+            // pipeline across pillars: four loads of 16 columns per pillar through two register buffers, the arithmetic
+            // on one buffer overlapping the load into the other, and the first load of the NEXT pillar issued -- when its
+            // accumulator is already complete -- before the last maximum of the current one.
 #pragma unroll 1
             for (int pr = 0; pr < kPairsPerUnit; ++pr) {
 #pragma unroll
                 for (int s = 0; s < kAccStages; ++s, ++jn) {
                     const uint32_t tph = (uint32_t)(jn >> 1) & 1u;
                     if (quad == 0) PTL(9 + g, jn, 0);
-                    if (!ready) mbar_wait_sa(tf_sa + 8u * s, tph);
-                    if (quad == 0) PTL(9 + g, jn, 1);
-                    tc_fence_after();
-                    float rm;
-#if P3P_EPI_LD == 32
-                    {
-                        float va[32], vb[32];
-                        tmem_ld32_issue(taddr_o + (uint32_t)(s * kAccCols), va);
-                        tmem_ld_wait(va);
-                        tmem_ld32_issue(taddr_o + (uint32_t)(s * kAccCols + 32), vb);
-                        ready = (jn + 1 < my_pillars) ? mbar_test_sa(tf_sa + 8u * (s ^ 1), (uint32_t)((jn + 1) >> 1) & 1u) : 0u;
-                        const float r0 = max32(va);
-                        tmem_ld_wait(vb);
-                        tc_fence_before();
-                        mbar_arrive_sa(te_sa + 8u * s);
-                        rm = fmaxf(r0, max32(vb));
-                    }
-#else
-                    {
-                        // four loads of 16 columns through two register buffers: the arithmetic on one buffer overlaps
-                        // with the load into the other
-                        float va[16], vb[16];
+                    if (!inflight) {
+                        if (!ready) mbar_wait_sa(tf_sa + 8u * s, tph);
+                        tc_fence_after();
                         tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols), va);
-                        tmem_ld_wait16(va);
-                        tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 16), vb);
-                        ready = (jn + 1 < my_pillars) ? mbar_test_sa(tf_sa + 8u * (s ^ 1), (uint32_t)((jn + 1) >> 1) & 1u) : 0u;
-                        const float r0 = max16(va);
-                        tmem_ld_wait16(vb);
-                        tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 32), va);
-                        const float r1 = max16(vb);
-                        tmem_ld_wait16(va);
-                        tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 48), vb);
-                        const float r2 = max16(va);
-                        tmem_ld_wait16(vb);
-                        tc_fence_before();
-                        mbar_arrive_sa(te_sa + 8u * s);
-                        rm = fmaxf(fmax3(r0, r1, r2), max16(vb));
                     }
-#endif
-                    my_rmax[(2 * pr + s) * 32] = rm;
+                    if (quad == 0) PTL(9 + g, jn, 1);
+                    tmem_ld_wait16(va);
+                    tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 16), vb);
+                    ready = (jn + 1 < my_pillars) ? mbar_test_sa(tf_sa + 8u * (s ^ 1), (uint32_t)((jn + 1) >> 1) & 1u) : 0u;
+                    const float r0 = max16(va);
+                    tmem_ld_wait16(vb);
+                    tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 32), va);
+                    const float r1 = max16(vb);
+                    tmem_ld_wait16(va);
+                    tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 48), vb);
+                    const float r2 = max16(va);
+                    tmem_ld_wait16(vb);
+                    tc_fence_before();
+                    mbar_arrive_sa(te_sa + 8u * s);
+                    // (the vote makes the decision warp-uniform: tcgen05.ld is a warp-wide instruction)
+                    inflight = __all_sync(0xffffffffu, ready != 0u) != 0;
+                    ready = inflight ? 1u : 0u;
+                    if (inflight) {
+                        tc_fence_after();
+                        tmem_ld16_issue(taddr_o + (uint32_t)((s ^ 1) * kAccCols), va);
+                    }
+                    sts_f32(rmax_sa + (uint32_t)((2 * pr + s) * 128), fmaxf(fmax3(r0, r1, r2), max16(vb)));
                     if (quad == 0) PTL(9 + g, jn, 2);
                 }
             }
             float rmax[kUnit];
 #pragma unroll
-            for (int i = 0; i < kUnit; ++i) rmax[i] = my_rmax[i * 32];
+            for (int i = 0; i < kUnit; ++i) rmax[i] = lds_f32(rmax_sa + (uint32_t)(i * 128));
             // ---- W1b' hmax of the unit's 8 items (one MMA per unit), bias, relu, the 8 cells ---------------------------
             float gv[8];
             mbar_wait_sa(gtf_sa, (uint32_t)j & 1u);
@@ -958,7 +954,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             tc_fence_before();
             mbar_arrive_sa(gte_sa);
             // which items hold a pillar: written by the front end before the pairs' operands were released
-            const uint2 vv = *reinterpret_cast<const uint2*>(sValid + ((j * kPairsPerUnit) & (kValidRing - 1)) * 2);
+            const uint2 vv = lds_u32x2(valid_sa + (uint32_t)(((j * kPairsPerUnit) & (kValidRing - 1)) * 2));
             float ob[kUnit];
 #pragma unroll
             for (int i = 0; i < kUnit; ++i) {
@@ -987,9 +983,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                         }
                     } else if (f32) {
                         // (B, ny nx, C) rows: a warp writes 32 consecutive channels of each of the unit's 8 cells
-                        float* dst = static_cast<float*>(a.out) + (int64_t)item0 * C + c;
+                        float* dst = rows_dst;
 #pragma unroll
-                        for (int i = 0; i < kUnit; ++i) dst[(int64_t)i * C] = ob[i];
+                        for (int i = 0; i < kUnit; ++i) { *dst = ob[i]; dst += C; }
                     } else {
                         unsigned short* dst = static_cast<unsigned short*>(a.out) + (int64_t)item0 * C + c;
 #pragma unroll
@@ -1016,6 +1012,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                     }
                 }
             }
+            rows_dst += rows_step;
             if (quad == 0) PTL(9 + g, jn - 1, 3);
         }
     }
