@@ -49,7 +49,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lidar", choices=["lidar", "fusion"])
+    ap.add_argument("--workload", default="lidar", choices=["lidar", "fusion", "fusion_layer"],
+                    help="lidar: voxelize + PFN + scatter -> tokens; fusion: + patch embed -> concat (B, 768, 28, 28); "
+                         "fusion_layer: + conv3x3 768 -> 384 + BN + ReLU -> tokens (SURVEY 8f rank 1)")
     ap.add_argument("--batch", type=int, default=16, help="tiles per GPU per step")
     ap.add_argument("--points", type=int, default=100_000, help="points per tile")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "tf32", "fp16", "bf16"])
@@ -66,6 +68,8 @@ def algorithmic_bytes_per_tile(n_points, workload):
     """LiDAR-only 12 N + 4 C ny nx; early fusion 12 N + 4*3*224*224 + 4*768*784 (fp32 I/O)."""
     if workload == "fusion":
         return 12 * n_points + 4 * 3 * 224 * 224 + 4 * 768 * HW
+    if workload == "fusion_layer":  # points + image in, fused tokens out (the concat is not an algorithmic output)
+        return 12 * n_points + 4 * 3 * 224 * 224 + 4 * C_FEAT * HW
     return 12 * n_points + 4 * C_FEAT * HW
 
 
@@ -234,8 +238,9 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args):
-    name = ("Pix2Poly LiDAR-only (PointPillars front end of lidar_pp_vit)" if args.workload == "lidar"
-            else "Pix2Poly early fusion (image patch embed + LiDAR pillars -> concat)")
+    name = {"lidar": "Pix2Poly LiDAR-only (PointPillars front end of lidar_pp_vit)",
+            "fusion": "Pix2Poly early fusion (image patch embed + LiDAR pillars -> concat)",
+            "fusion_layer": "Pix2Poly early fusion through fusion_layer (patch embed + LiDAR pillars + conv3x3 768->384 + BN + ReLU -> tokens)"}[args.workload]
     return {"workload": f"{name}, synthetic 224px tiles, {args.points} pts/tile, batch {args.batch} per GPU",
             "tiles_per_gpu": args.batch, "points_per_tile": args.points, "max_points_per_voxel": args.max_points_per_voxel,
             "precision": args.precision,
@@ -258,14 +263,21 @@ class Workload:
         sd, sdi = synth.synth_weights(0)
         self.enc.load_state_dict(sd)
         self.fusion = None
-        if workload == "fusion":
+        if workload in ("fusion", "fusion_layer"):
             from pixelspointspolygons_b200.fusion import EarlyFusionFrontEnd
 
             self.fusion = EarlyFusionFrontEnd(cfg).to(dev).eval()
             self.fusion.lidar_embed.load_state_dict(sd)
             self.fusion.image_embed.load_state_dict(sdi)
+            with torch.no_grad():  # seeded fusion_layer weights (conv ~ N(0, 1/fan_in), BN like synth_weights)
+                g = torch.Generator().manual_seed(1)
+                fl = self.fusion.fusion_layer
+                fl[0].weight.copy_((torch.randn(fl[0].weight.shape, generator=g) / (9 * 768) ** 0.5).to(dev))
+                fl[0].bias.copy_((torch.randn(C_FEAT, generator=g) * 0.1).to(dev))
+                fl[1].weight.copy_((torch.rand(C_FEAT, generator=g) + 0.5).to(dev))
+                fl[1].running_var.copy_((torch.rand(C_FEAT, generator=g) + 0.5).to(dev))
         # enough rotating sets that consecutive uses of a set are > L2 apart
-        per_set = 12 * N * B + (4 * 768 * HW * B + 4 * 3 * 224 * 224 * B if workload == "fusion" else 4 * C_FEAT * HW * B)
+        per_set = 12 * N * B + (4 * 768 * HW * B + 4 * 3 * 224 * 224 * B if self.fusion is not None else 4 * C_FEAT * HW * B)
         self.sets = sets = max(2, sets, -(-(160 << 20) // per_set))
         host_tiles = [[synth.synth_tile(N, 1000 * (1 + rank) + 16 * s + i, clustered=(i % 2 == 1)) for i in range(B)]
                       for s in range(min(sets, 8))]
@@ -283,7 +295,11 @@ class Workload:
             imgs = [torch.rand(B, 3, 224, 224) for _ in range(min(sets, 8))]
             self.pinned_img = [p.pin_memory() for p in imgs] if keep_host else None
             self.dev_img = [imgs[s % len(imgs)].to(dev) for s in range(sets)]
-            self.outs = [torch.empty(B, 2 * C_FEAT, 28, 28, device=dev) for _ in range(sets)]
+            if workload == "fusion_layer":
+                self.x16 = [torch.empty(B, 28, 28, 2 * C_FEAT, dtype=self.fusion.fusion_layer.operand_dtype, device=dev) for _ in range(sets)]
+                self.outs = [torch.empty(B, HW, C_FEAT, device=dev) for _ in range(sets)]
+            else:
+                self.outs = [torch.empty(B, 2 * C_FEAT, 28, 28, device=dev) for _ in range(sets)]
         else:
             self.outs = [torch.empty(B, HW, C_FEAT, device=dev) for _ in range(sets)]
         self._lib = _lib
@@ -304,7 +320,9 @@ class Workload:
 
     def step(self, i):
         s = i % self.sets
-        if self.fusion is not None:
+        if self.workload == "fusion_layer":
+            self.fusion.forward_tokens_into(self.dev_img[s], self.dev_x[s], self.x16[s], self.outs[s], lidar_zero=False)
+        elif self.fusion is not None:
             self.fusion.forward_into(self.dev_img[s], self.dev_x[s], self.outs[s])
         else:
             self.enc.encode_into(self.dev_x[s], self.outs[s], self._lib.P3P_LAYOUT_NLC)
@@ -317,7 +335,8 @@ class Workload:
 
     @property
     def launches_per_step(self):
-        return 2 if self.fusion is None else 3  # voxelize + PFN (+ patch embed); the counter memset is not a kernel
+        # voxelize + PFN (+ patch embed (+ fusion convolution)); the counter memset is not a kernel
+        return 2 if self.fusion is None else (4 if self.workload == "fusion_layer" else 3)
 
     def time_steps(self, steps, first=0):
         """Device time (ms) of `steps` back-to-back steps on the current stream."""
@@ -338,6 +357,27 @@ class Workload:
         return total_steps, total_ms
 
 
+def conv_roofline(w, peaks):
+    """The fusion convolution alone (resident 16-bit input of the last step of every set): FLOPs / CUDA-event time."""
+    fl = w.fusion.fusion_layer
+    B = w.B
+    for i in range(3):
+        fl.forward_nhwc(w.x16[i % w.sets], w.outs[i % w.sets], 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 40
+    e0.record()
+    for i in range(n):
+        fl.forward_nhwc(w.x16[i % w.sets], w.outs[i % w.sets], 1)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = 2.0 * B * HW * C_FEAT * 9 * 2 * C_FEAT
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    return {"kernel": "conv3x3_tc_kernel", "bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+            "frac": flops / (ms * 1e-3) / 1e12 / peak, "ms_per_launch": ms, "flops_per_launch": flops,
+            "what": "implicit GEMM 784 B x 6912 x 384 (16-bit operands, fp32 accumulate), launched back to back"}
+
+
 def sub_result(dev, rank, workload, precision, B, N, M, seconds=0.4):
     """A secondary configuration, device-timed for ~`seconds` after a warm-up (CUDA-graph replay, rotating sets)."""
     try:
@@ -346,6 +386,13 @@ def sub_result(dev, rank, workload, precision, B, N, M, seconds=0.4):
         steps, ms = w.time_for(seconds, chunk=64)
         out = {"workload": workload, "precision": precision, "tiles_per_gpu": B, "points_per_tile": N, "max_points_per_voxel": M,
                "ms_per_step": ms / steps, "tiles_per_s_per_gpu": B * steps / (ms * 1e-3), "steps": steps, "sets": w.sets}
+        if workload == "fusion_layer":
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            out["conv_roofline"] = conv_roofline(w, peaks)
         del w
         torch.cuda.empty_cache()
         return out
@@ -443,7 +490,10 @@ def main():
         b = i % nbuf
         main_stream.wait_event(copied[b])
         x = torch.nested.nested_tensor_from_jagged(d_vals[b], d_offs[b])
-        y = fusion(d_img[b], x) if fusion is not None else enc(x, return_flattened=True)
+        if args.workload == "fusion_layer":
+            y = fusion.forward_tokens(d_img[b], x, lidar_zero=False)
+        else:
+            y = fusion(d_img[b], x) if fusion is not None else enc(x, return_flattened=True)
         consumed[b].record(main_stream)
         if full:
             h_full[b].copy_(y.reshape(-1), non_blocking=True)
@@ -537,7 +587,8 @@ def main():
         del d_vals, d_offs, d_img, h_full
         torch.cuda.empty_cache()
         plan = [("lidar", "tf32", B, N, M), ("lidar", "bf16", B, N, M), ("fusion", args.precision, 16, N, M),
-                ("fusion", args.precision, 8, N, M), ("fusion", "tf32", 16, N, M), ("lidar", args.precision, 32, N, M),
+                ("fusion", args.precision, 8, N, M), ("fusion", "tf32", 16, N, M), ("fusion_layer", args.precision, 16, N, M),
+                ("fusion_layer", args.precision, 8, N, M), ("lidar", args.precision, 32, N, M),
                 ("lidar", args.precision, 16, 10_000, M), ("lidar", args.precision, 16, 400_000, M),
                 ("lidar", args.precision, 16, N, 128)]
         for wl, prec, b, n, m in plan:

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define P3P_VERSION 100
+#define P3P_VERSION 200
 
 enum {
     P3P_OK = 0,
@@ -67,7 +67,7 @@ enum {
     P3P_LAYOUT_NLC = 1   /* (B, ny*nx, C) contiguous tokens == x.flatten(2).transpose(1,2) values */
 };
 
-enum { P3P_DTYPE_F32 = 0, P3P_DTYPE_BF16 = 1 };
+enum { P3P_DTYPE_F32 = 0, P3P_DTYPE_BF16 = 1, P3P_DTYPE_F16 = 2 };
 
 /*
  * Voxel grid and limits.  Mirrors the constructor arguments the reference derives from
@@ -119,6 +119,20 @@ typedef struct p3p_voxel_outputs {
     int32_t* cell_owner;       /* (B, ny*nx) voxel ordinal that owns each canvas cell (last writer), -1 if empty */
 } p3p_voxel_outputs;
 
+/* Raw parameters of a 3x3 convolution followed by an eval-mode BatchNorm2d, fp32 device pointers.  Names are the
+ * reference's state_dict keys under `fusion_layer.{0,1}.` / `proj.{1,2}.` (nn.Sequential indices). */
+typedef struct p3p_conv_params {
+    const float* weight;      /* (Cout, Cin, 3, 3)  0.weight */
+    const float* bias;        /* (Cout) or NULL     0.bias */
+    const float* norm_weight; /* (Cout) or NULL (no BatchNorm)  1.weight */
+    const float* norm_bias;   /* (Cout)             1.bias */
+    const float* norm_mean;   /* (Cout)             1.running_mean */
+    const float* norm_var;    /* (Cout)             1.running_var */
+    float eps;                /* BatchNorm2d eps (1e-5) */
+    int32_t in_channels;      /* Cin: a multiple of 64 */
+    int32_t out_channels;     /* Cout */
+} p3p_conv_params;
+
 /* Per-tile constants of p3p_las_to_pixels (a device array of num_tiles entries). */
 typedef struct p3p_las_tile {
     double scale[3];         /* las.header.scales */
@@ -169,8 +183,8 @@ int p3p_pillar_features(const p3p_grid* grid, int32_t num_tiles, int64_t total_p
 
 /*
  * The fused hot path: voxelize -> PFN -> scatter, one call per batch.
- * out: NCHW (B, c_total, ny, nx) written at channels [c_offset, c_offset + C), or NLC (B, ny*nx, C)
- * (c_total / c_offset ignored).  Every cell of the LiDAR channels is written (empty cells = 0), so the
+ * out: NCHW (B, c_total, ny, nx) written at channels [c_offset, c_offset + C), or NLC rows (B, ny*nx, C) when
+ * c_total == 0, (B, ny*nx, c_total) rows at channel c_offset otherwise; out_dtype fp32, bf16 or fp16.  Every cell of the LiDAR channels is written (empty cells = 0), so the
  * buffer needs no memset.  lidar_zero != 0 reproduces `x_lidar * 0.0` (LiDAR dropout) without running
  * the encoder.
  */
@@ -195,12 +209,13 @@ int p3p_encode_tokens(const float* points, int32_t point_stride, const int64_t* 
 
 /*
  * Image patch embedding: Conv2d(in_chans, C, kernel=P, stride=P, bias) on (B, in_chans, H, W) fp32,
- * written NCHW into channels [c_offset, c_offset + C) of out (B, c_total, H/P, W/P).
+ * written into channels [c_offset, c_offset + C) of out: P3P_LAYOUT_NCHW (B, c_total, H/P, W/P) or P3P_LAYOUT_NLC
+ * channels-last rows (B, H/P * W/P, c_total) -- with a 16-bit out_dtype the image half of the fusion convolution's input.
  * weight: (C, in_chans, P, P) fp32; bias: (C) fp32 or NULL.
  */
 int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, int32_t height, int32_t width,
                     int32_t patch, const float* weight, const float* bias, int32_t channels, int32_t precision,
-                    void* out, int32_t out_dtype, int32_t c_total, int32_t c_offset, void* stream);
+                    void* out, int32_t out_dtype, int32_t out_layout, int32_t c_total, int32_t c_offset, void* stream);
 
 /*
  * LiDAR input front end: raw LAS integer coordinates of a jagged batch -> the (total_points, 3)
@@ -213,6 +228,34 @@ int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, in
 int p3p_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, const int64_t* tile_offsets, int32_t num_tiles,
                       int64_t total_points, const p3p_las_tile* tiles, double z_hi, int32_t* minmax_ws, float* points,
                       void* stream);
+
+/*
+ * SURVEY 8f rank 1 -- the reference's `fusion_layer` (early_fusion_vit.py:75-79,123; early_fusion_vit_cnn.py:72-76,94):
+ *     x = ReLU(BatchNorm2d(Conv2d(Cin, Cout, kernel_size=3, padding=1)(x)))        [ .flatten(2).transpose(1, 2) ]
+ * as an implicit GEMM on the tensor cores.  The input is 16-bit channels-last, x: (B, H, W, Cin) fp16 (precision
+ * P3P_PRECISION_FP16) or bf16 (P3P_PRECISION_BF16); p3p_encode / p3p_patch_embed write their halves of it directly
+ * (out_layout P3P_LAYOUT_NLC with c_total = Cin and dtype P3P_DTYPE_F16 / BF16), p3p_nchw_to_nhwc16 converts an existing
+ * fp32 NCHW tensor.  out: fp32, P3P_LAYOUT_NLC = token rows (B, H W, c_total) at channel c_offset (the flatten +
+ * transpose of the reference is the store address), or P3P_LAYOUT_NCHW (B, c_total, H, W).
+ * The same call with other sizes is the convolution of the `proj` tails (rank 5) behind p3p_upsample_bilinear_nhwc16.
+ */
+size_t p3p_conv3x3_blob_bytes(int32_t in_channels, int32_t out_channels);
+int p3p_conv3x3_prepare(const p3p_conv_params* params, int32_t precision, void* blob, size_t blob_bytes, void* stream);
+int p3p_conv3x3(const void* x, int32_t num_tiles, int32_t height, int32_t width, int32_t in_channels, const void* blob,
+                int32_t out_channels, int32_t precision, int32_t relu, float* out, int32_t out_layout, int32_t c_total,
+                int32_t c_offset, void* stream);
+
+/* fp32 NCHW (B, C, H, W) -> 16-bit channels-last (B, H, W, c_total) at channel offset c_offset. */
+int p3p_nchw_to_nhwc16(const float* x, int32_t num_tiles, int32_t channels, int32_t height, int32_t width, int32_t precision,
+                       void* out, int32_t c_total, int32_t c_offset, void* stream);
+
+/*
+ * nn.Upsample(size=(out_h, out_w), mode='bilinear', align_corners=False) of fp32 token rows x: (B, h w, C) with
+ * src_batch_stride floats between tiles (the ViT output with its class token skipped; pointpillars_vit_cnn.py:31-36,
+ * early_fusion_vit_cnn.py:97-102) into 16-bit channels-last out: (B, out_h, out_w, C), the input of p3p_conv3x3.
+ */
+int p3p_upsample_bilinear_nhwc16(const float* x, int32_t num_tiles, int32_t h, int32_t w, int32_t channels,
+                                 int64_t src_batch_stride, int32_t out_h, int32_t out_w, int32_t precision, void* out, void* stream);
 
 /*
  * Measurement hooks (bench.py's roofline leg; no reference counterpart).  Between begin and end every

@@ -9,13 +9,14 @@ from .build import LIB_PATH
 
 P3P_PRECISION = {"fp32": 0, "tf32": 1, "bf16": 2, "fp16": 3}
 P3P_LAYOUT_NCHW, P3P_LAYOUT_NLC = 0, 1
-P3P_DTYPE_F32, P3P_DTYPE_BF16 = 0, 1
+P3P_DTYPE_F32, P3P_DTYPE_BF16, P3P_DTYPE_F16 = 0, 1, 2
 P3P_GRID_DROP_OVERFLOW = 1
 
 EXPORTED = [
     "p3p_last_error", "p3p_version", "p3p_workspace_bytes", "p3p_pfn_blob_bytes", "p3p_pfn_prepare",
     "p3p_voxelize", "p3p_pillar_features", "p3p_encode", "p3p_encode_tokens", "p3p_patch_embed", "p3p_las_to_pixels",
-    "p3p_profile_begin", "p3p_profile_end",
+    "p3p_profile_begin", "p3p_profile_end", "p3p_conv3x3_blob_bytes", "p3p_conv3x3_prepare", "p3p_conv3x3",
+    "p3p_nchw_to_nhwc16", "p3p_upsample_bilinear_nhwc16",
 ]
 
 
@@ -40,6 +41,11 @@ class PfnParams(C.Structure):
         "linear0_weight", "norm0_weight", "norm0_bias", "norm0_mean", "norm0_var",
         "linear1_weight", "norm1_weight", "norm1_bias", "norm1_mean", "norm1_var")] + [
         ("eps", C.c_float), ("channels", C.c_int32), ("center_alias", C.c_int32)]
+
+
+class ConvParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("weight", "bias", "norm_weight", "norm_bias", "norm_mean", "norm_var")] + [
+        ("eps", C.c_float), ("in_channels", C.c_int32), ("out_channels", C.c_int32)]
 
 
 class VoxelOutputs(C.Structure):
@@ -87,7 +93,17 @@ def lib():
     l.p3p_las_to_pixels.restype = C.c_int
     l.p3p_las_to_pixels.argtypes = [vp, vp, vp, vp, i32, i64, vp, C.c_double, vp, vp, vp]
     l.p3p_patch_embed.restype = C.c_int
-    l.p3p_patch_embed.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp]
+    l.p3p_patch_embed.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp]
+    l.p3p_conv3x3_blob_bytes.restype = sz
+    l.p3p_conv3x3_blob_bytes.argtypes = [i32, i32]
+    l.p3p_conv3x3_prepare.restype = C.c_int
+    l.p3p_conv3x3_prepare.argtypes = [C.POINTER(ConvParams), i32, vp, sz, vp]
+    l.p3p_conv3x3.restype = C.c_int
+    l.p3p_conv3x3.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, i32, i32, i32, vp]
+    l.p3p_nchw_to_nhwc16.restype = C.c_int
+    l.p3p_nchw_to_nhwc16.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp]
+    l.p3p_upsample_bilinear_nhwc16.restype = C.c_int
+    l.p3p_upsample_bilinear_nhwc16.argtypes = [vp, i32, i32, i32, i32, i64, i32, i32, i32, vp, vp]
     l.p3p_profile_begin.restype = C.c_int
     l.p3p_profile_begin.argtypes = [i32]
     l.p3p_profile_end.restype = C.c_int

@@ -246,6 +246,8 @@ static void fill_pfn_args(PfnArgs* a, const GridDev& g, const WsPtrs& ws, const 
     a->blob = static_cast<const char*>(blob);
     a->bl = bl;
     a->B = B;
+    a->row_stride = bl.C;
+    a->row_offset = 0;
 }
 
 int p3p_pillar_features(const p3p_grid* grid, int32_t num_tiles, int64_t total_points, const void* blob, int32_t channels,
@@ -289,8 +291,8 @@ int p3p_encode(const float* points, int32_t point_stride, const int64_t* tile_of
     if (!out || !aligned16(out)) return fail(P3P_ERR_INVALID_ARGUMENT, "out null or misaligned");
     if (!lidar_zero && (!blob || !aligned16(blob))) return fail(P3P_ERR_INVALID_ARGUMENT, "blob null or misaligned");
     if (out_layout != P3P_LAYOUT_NCHW && out_layout != P3P_LAYOUT_NLC) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown layout %d", out_layout);
-    if (out_dtype != P3P_DTYPE_F32 && out_dtype != P3P_DTYPE_BF16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown dtype %d", out_dtype);
-    if (out_layout == P3P_LAYOUT_NCHW && (c_offset < 0 || c_offset + channels > c_total))
+    if (out_dtype != P3P_DTYPE_F32 && out_dtype != P3P_DTYPE_BF16 && out_dtype != P3P_DTYPE_F16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown dtype %d", out_dtype);
+    if ((out_layout == P3P_LAYOUT_NCHW || c_total > 0) && (c_offset < 0 || c_offset + channels > c_total))
         return fail(P3P_ERR_INVALID_ARGUMENT, "channels [%d, %d) outside c_total %d", c_offset, c_offset + channels, c_total);
     if (num_tiles == 0) return P3P_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -304,6 +306,10 @@ int p3p_encode(const float* points, int32_t point_stride, const int64_t* tile_of
     a.out_dtype = out_dtype;
     a.c_total = c_total;
     a.c_offset = c_offset;
+    if (out_layout == P3P_LAYOUT_NLC && c_total > 0) {  // rows of a wider channels-last buffer (the fusion convolution's input)
+        a.row_stride = c_total;
+        a.row_offset = c_offset;
+    }
     if (lidar_zero) return launch_zero_lidar(a, st);  // `x_lidar * 0.0` (early_fusion_vit.py:113-119)
     cudaEvent_t* ev = nullptr;
     if (g_prof.on && (size_t)(g_prof.used + 1) * 3 <= g_prof.ev.size()) ev = g_prof.ev.data() + (size_t)g_prof.used * 3;
@@ -366,6 +372,55 @@ int p3p_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, cons
                                 static_cast<cudaStream_t>(stream));
 }
 
+size_t p3p_conv3x3_blob_bytes(int32_t in_channels, int32_t out_channels) {
+    if (in_channels < 1 || out_channels < 1) return 0;
+    return conv3x3_blob_bytes(in_channels, out_channels);
+}
+
+int p3p_conv3x3_prepare(const p3p_conv_params* p, int32_t precision, void* blob, size_t blob_bytes, void* stream) {
+    if (!p || !blob || !p->weight) return fail(P3P_ERR_INVALID_ARGUMENT, "null params, weight or blob");
+    if (p->norm_weight && (!p->norm_bias || !p->norm_mean || !p->norm_var)) return fail(P3P_ERR_INVALID_ARGUMENT, "incomplete BatchNorm parameters");
+    if (p->in_channels < 1 || p->out_channels < 1) return fail(P3P_ERR_INVALID_ARGUMENT, "channels must be positive");
+    if (precision != P3P_PRECISION_BF16 && precision != P3P_PRECISION_FP16) return fail(P3P_ERR_UNSUPPORTED, "conv3x3 precision must be bf16 or fp16");
+    if (!aligned16(blob)) return fail(P3P_ERR_INVALID_ARGUMENT, "blob must be 16-byte aligned");
+    const size_t need = conv3x3_blob_bytes(p->in_channels, p->out_channels);
+    if (blob_bytes < need) return fail(P3P_ERR_WORKSPACE, "blob needs %zu bytes, got %zu", need, blob_bytes);
+    return launch_conv3x3_prepare(p, precision, blob, static_cast<cudaStream_t>(stream));
+}
+
+int p3p_conv3x3(const void* x, int32_t num_tiles, int32_t height, int32_t width, int32_t in_channels, const void* blob,
+                int32_t out_channels, int32_t precision, int32_t relu, float* out, int32_t out_layout, int32_t c_total,
+                int32_t c_offset, void* stream) {
+    if (num_tiles < 0 || height < 1 || width < 1 || in_channels < 1 || out_channels < 1) return fail(P3P_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (num_tiles == 0) return P3P_OK;
+    if (!x || !blob || !out) return fail(P3P_ERR_INVALID_ARGUMENT, "null x, blob or out");
+    if (!aligned16(x) || !aligned16(blob) || !aligned16(out)) return fail(P3P_ERR_INVALID_ARGUMENT, "misaligned pointer");
+    if (out_layout != P3P_LAYOUT_NCHW && out_layout != P3P_LAYOUT_NLC) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown layout %d", out_layout);
+    if (c_offset < 0 || c_offset + out_channels > c_total) return fail(P3P_ERR_INVALID_ARGUMENT, "channels [%d, %d) outside c_total %d", c_offset, c_offset + out_channels, c_total);
+    return launch_conv3x3(x, num_tiles, height, width, in_channels, blob, out_channels, precision, relu, out, out_layout, c_total, c_offset,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int p3p_nchw_to_nhwc16(const float* x, int32_t num_tiles, int32_t channels, int32_t height, int32_t width, int32_t precision,
+                       void* out, int32_t c_total, int32_t c_offset, void* stream) {
+    if (num_tiles < 0 || channels < 1 || height < 1 || width < 1) return fail(P3P_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (num_tiles == 0) return P3P_OK;
+    if (!x || !out) return fail(P3P_ERR_INVALID_ARGUMENT, "null x or out");
+    if (precision != P3P_PRECISION_BF16 && precision != P3P_PRECISION_FP16) return fail(P3P_ERR_UNSUPPORTED, "precision must be bf16 or fp16");
+    if (c_offset < 0 || c_offset + channels > c_total) return fail(P3P_ERR_INVALID_ARGUMENT, "channels outside c_total");
+    return launch_nchw_to_nhwc16(x, num_tiles, channels, height, width, precision, out, c_total, c_offset, static_cast<cudaStream_t>(stream));
+}
+
+int p3p_upsample_bilinear_nhwc16(const float* x, int32_t num_tiles, int32_t h, int32_t w, int32_t channels, int64_t src_batch_stride,
+                                 int32_t out_h, int32_t out_w, int32_t precision, void* out, void* stream) {
+    if (num_tiles < 0 || h < 1 || w < 1 || channels < 1 || out_h < 1 || out_w < 1) return fail(P3P_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (num_tiles == 0) return P3P_OK;
+    if (!x || !out) return fail(P3P_ERR_INVALID_ARGUMENT, "null x or out");
+    if (precision != P3P_PRECISION_BF16 && precision != P3P_PRECISION_FP16) return fail(P3P_ERR_UNSUPPORTED, "precision must be bf16 or fp16");
+    return launch_upsample_bilinear_nhwc16(x, num_tiles, h, w, channels, src_batch_stride, out_h, out_w, precision, out,
+                                           static_cast<cudaStream_t>(stream));
+}
+
 int p3p_profile_begin(int32_t max_records) {
     if (max_records < 1 || max_records > 100000) return fail(P3P_ERR_INVALID_ARGUMENT, "max_records %d", max_records);
     for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
@@ -399,21 +454,22 @@ int p3p_profile_end(float* ms_voxelize, float* ms_pfn, int32_t capacity, int32_t
 
 int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, int32_t height, int32_t width,
                     int32_t patch, const float* weight, const float* bias, int32_t channels, int32_t precision, void* out,
-                    int32_t out_dtype, int32_t c_total, int32_t c_offset, void* stream) {
+                    int32_t out_dtype, int32_t out_layout, int32_t c_total, int32_t c_offset, void* stream) {
     if (num_tiles < 0) return fail(P3P_ERR_INVALID_ARGUMENT, "num_tiles %d", num_tiles);
     if (in_chans < 1 || height < 1 || width < 1 || patch < 1 || channels < 1)
         return fail(P3P_ERR_INVALID_ARGUMENT, "in_chans, height, width, patch and channels must be positive");
     if (height % patch != 0 || width % patch != 0)
         return fail(P3P_ERR_INVALID_ARGUMENT, "image %d x %d is not a whole number of %d-px patches", height, width, patch);
     if (precision < P3P_PRECISION_FP32 || precision > P3P_PRECISION_FP16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
-    if (out_dtype != P3P_DTYPE_F32 && out_dtype != P3P_DTYPE_BF16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown dtype %d", out_dtype);
+    if (out_dtype != P3P_DTYPE_F32 && out_dtype != P3P_DTYPE_BF16 && out_dtype != P3P_DTYPE_F16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown dtype %d", out_dtype);
+    if (out_layout != P3P_LAYOUT_NCHW && out_layout != P3P_LAYOUT_NLC) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown layout %d", out_layout);
     if (c_offset < 0 || c_offset + channels > c_total)
         return fail(P3P_ERR_INVALID_ARGUMENT, "channels [%d, %d) outside c_total %d", c_offset, c_offset + channels, c_total);
     if (num_tiles == 0) return P3P_OK;
     if (!images || !weight || !out) return fail(P3P_ERR_INVALID_ARGUMENT, "null images, weight or out");
     if (!aligned16(images) || !aligned16(weight) || !aligned16(out)) return fail(P3P_ERR_INVALID_ARGUMENT, "misaligned pointer");
     return launch_patch_embed(images, num_tiles, in_chans, height, width, patch, weight, bias, channels, precision, out, out_dtype,
-                              c_total, c_offset, static_cast<cudaStream_t>(stream));
+                              out_layout, c_total, c_offset, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -148,6 +148,7 @@ struct PfnArgs {
     int out_layout;  // P3P_LAYOUT_*
     int out_dtype;   // P3P_DTYPE_*
     int c_total, c_offset;
+    int row_stride, row_offset;  // rows layouts: out[item * row_stride + row_offset + c] (row_stride = C when the rows are dense)
     // token sequence output (p3p_encode_tokens): rows of C channels, 1 + items_per_tile rows per tile, row 0 = class
     // token; pos_embed (1 + items_per_tile, C) is added to every row.  token_rows == 0: off
     const float* pos_embed;
@@ -164,10 +165,17 @@ int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st);
 int launch_zero_lidar(const PfnArgs& a, cudaStream_t st);
 int launch_cls_rows(const PfnArgs& a, const float* cls_token, cudaStream_t st);
 int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, int P, const float* weight,
-                       const float* bias, int C, int precision, void* out, int out_dtype, int c_total, int c_offset,
+                       const float* bias, int C, int precision, void* out, int out_dtype, int out_layout, int c_total, int c_offset,
                        cudaStream_t st);
 int launch_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, const int64_t* offsets, int B, int64_t total,
                          const p3p_las_tile* tiles, double z_hi, int32_t* mm, float* out, cudaStream_t st);
+size_t conv3x3_blob_bytes(int Cin, int Cout);
+int launch_conv3x3_prepare(const p3p_conv_params* p, int precision, void* blob, cudaStream_t st);
+int launch_conv3x3(const void* x, int B, int H, int W, int Cin, const void* blob, int Cout, int precision, int relu, float* out,
+                   int out_layout, int c_total, int c_offset, cudaStream_t st);
+int launch_nchw_to_nhwc16(const float* x, int B, int C, int H, int W, int precision, void* out, int c_total, int c_offset, cudaStream_t st);
+int launch_upsample_bilinear_nhwc16(const float* x, int B, int h, int w, int C, int64_t src_batch_stride, int H, int W, int precision,
+                                    void* out, cudaStream_t st);
 int device_sm_count();
 
 // ----------------------------------------------------------------------------------------------
@@ -428,6 +436,14 @@ __device__ __forceinline__ float warp_max_f32(float v) {
 __device__ __forceinline__ uint32_t to_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned short to_16bit(float v, int dtype) {  // P3P_DTYPE_BF16 / P3P_DTYPE_F16
+    unsigned short r;
+    if (dtype == P3P_DTYPE_F16)
+        asm("cvt.rn.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    else
+        asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(v));
     return r;
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

@@ -25,7 +25,7 @@ __device__ __forceinline__ void store_out(void* out, int out_dtype, int64_t idx,
     if (out_dtype == P3P_DTYPE_F32)
         static_cast<float*>(out)[idx] = v;
     else
-        static_cast<unsigned short*>(out)[idx] = (unsigned short)(pack_bf16(v, 0.f) & 0xFFFF);
+        static_cast<unsigned short*>(out)[idx] = to_16bit(v, out_dtype);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -33,7 +33,7 @@ __device__ __forceinline__ void store_out(void* out, int out_dtype, int64_t idx,
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 patch_embed_simt_kernel(const float* __restrict__ img, int in_chans, int H, int W, int P, const float* __restrict__ weight,
-                        const float* __restrict__ bias, int C, void* out, int out_dtype, int c_total, int c_offset) {
+                        const float* __restrict__ bias, int C, void* out, int out_dtype, int out_layout, int c_total, int c_offset) {
     extern __shared__ float patch[];  // [in_chans * P * P]
     const int nx = W / P, ny = H / P;
     const int cell = blockIdx.x, b = blockIdx.y;
@@ -49,7 +49,9 @@ patch_embed_simt_kernel(const float* __restrict__ img, int in_chans, int H, int 
         float acc = 0.f;
         for (int k = 0; k < K; ++k) acc = __fmaf_rn(w[k], patch[k], acc);
         if (bias) acc += bias[ch];
-        store_out(out, out_dtype, ((int64_t)b * c_total + c_offset + ch) * (ny * nx) + cell, acc);
+        const int64_t idx = out_layout == P3P_LAYOUT_NLC ? ((int64_t)b * (ny * nx) + cell) * c_total + c_offset + ch
+                                                         : ((int64_t)b * c_total + c_offset + ch) * (ny * nx) + cell;
+        store_out(out, out_dtype, idx, acc);
     }
 }
 
@@ -66,7 +68,7 @@ struct PeArgs {
     int in_chans, H, W, C, nx, ny;
     int rows;       // cell rows per CTA
     int N;          // rows * nx: MMA N (multiple of 16, <= 128)
-    int out_dtype, c_total, c_offset;
+    int out_dtype, out_layout, c_total, c_offset;
 };
 
 // Operand rows are K-major and split into 128-byte chunks (SWIZZLE_128B atoms, 8 rows x 128 B); chunk q of a tile
@@ -215,16 +217,19 @@ __global__ void __launch_bounds__(kPeThreads, 1) patch_embed_tc_kernel(PeArgs a)
             float v[16];
             tmem_ld16_wait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(blk * 16), v);
             if (ch < a.C) {
-                if (a.out_dtype == P3P_DTYPE_F32) {
+                if (a.out_layout == P3P_LAYOUT_NLC) {
+                    // channels-last rows (B, ny nx, c_total): a warp writes 32 consecutive channels of one cell per store
+                    const int64_t r0 = ((int64_t)b * a.ny * a.nx + (int64_t)cy0 * a.nx + blk * 16) * a.c_total + a.c_offset + ch;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) store_out(a.out, a.out_dtype, r0 + (int64_t)i * a.c_total, v[i] + bv);
+                } else if (a.out_dtype == P3P_DTYPE_F32) {
                     float4* dst = reinterpret_cast<float4*>(static_cast<float*>(a.out) + row0 + blk * 16);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i] + bv, v[4 * i + 1] + bv, v[4 * i + 2] + bv, v[4 * i + 3] + bv);
                 } else {
-                    uint4* dst = reinterpret_cast<uint4*>(static_cast<unsigned short*>(a.out) + row0 + blk * 16);
+                    unsigned short* dst = static_cast<unsigned short*>(a.out) + row0 + blk * 16;
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        dst[i] = make_uint4(pack_bf16(v[8 * i] + bv, v[8 * i + 1] + bv), pack_bf16(v[8 * i + 2] + bv, v[8 * i + 3] + bv),
-                                            pack_bf16(v[8 * i + 4] + bv, v[8 * i + 5] + bv), pack_bf16(v[8 * i + 6] + bv, v[8 * i + 7] + bv));
+                    for (int i = 0; i < 16; ++i) dst[i] = to_16bit(v[i] + bv, a.out_dtype);
                 }
             }
         }
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(kPeThreads, 1) patch_embed_tc_kernel(PeArgs a)
 }  // namespace
 
 int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, int P, const float* weight, const float* bias,
-                       int C, int precision, void* out, int out_dtype, int c_total, int c_offset, cudaStream_t st) {
+                       int C, int precision, void* out, int out_dtype, int out_layout, int c_total, int c_offset, cudaStream_t st) {
     if (B <= 0) return P3P_OK;
     const int nx = W / P, ny = H / P;
     const bool tf32 = (precision != P3P_PRECISION_BF16 && precision != P3P_PRECISION_FP16);
@@ -255,18 +260,15 @@ int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, i
     const size_t smem = 1024 + (128 + (size_t)rows * nx) * K * esize;
     const bool k_ok = tf32 ? (K % 32 == 0) : (K % 64 == 0);
     if (rows > 0 && k_ok && smem <= 200 * 1024 && ((size_t)ny * nx * (out_dtype == P3P_DTYPE_F32 ? 4 : 2)) % 16 == 0) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<P3P_PRECISION_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<P3P_PRECISION_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<P3P_PRECISION_FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done = true;
-        }
+        // (the attribute belongs to the current device's context: set per launch, it is cheap)
+        P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<P3P_PRECISION_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<P3P_PRECISION_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        P3P_CUDA_CHECK(cudaFuncSetAttribute(patch_embed_tc_kernel<P3P_PRECISION_FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         PeArgs a;
         a.img = images; a.weight = weight; a.bias = bias; a.out = out;
         a.in_chans = in_chans; a.H = H; a.W = W; a.C = C; a.nx = nx; a.ny = ny;
         a.rows = rows; a.N = rows * nx;
-        a.out_dtype = out_dtype; a.c_total = c_total; a.c_offset = c_offset;
+        a.out_dtype = out_dtype; a.out_layout = out_layout; a.c_total = c_total; a.c_offset = c_offset;
         dim3 grid((unsigned)(ny / rows), (unsigned)((C + 127) / 128), (unsigned)B);
         if (tf32)
             patch_embed_tc_kernel<P3P_PRECISION_TF32><<<grid, kPeThreads, smem, st>>>(a);
@@ -280,7 +282,7 @@ int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, i
     const size_t smem_simt = (size_t)in_chans * P * P * sizeof(float);
     if (smem_simt > 48 * 1024) return fail(P3P_ERR_UNSUPPORTED, "patch of %d x %d x %d values exceeds the shared-memory budget", in_chans, P, P);
     dim3 grid((unsigned)(ny * nx), (unsigned)B);
-    patch_embed_simt_kernel<<<grid, 128, smem_simt, st>>>(images, in_chans, H, W, P, weight, bias, C, out, out_dtype, c_total, c_offset);
+    patch_embed_simt_kernel<<<grid, 128, smem_simt, st>>>(images, in_chans, H, W, P, weight, bias, C, out, out_dtype, out_layout, c_total, c_offset);
     P3P_CUDA_CHECK(cudaGetLastError());
     return P3P_OK;
 }

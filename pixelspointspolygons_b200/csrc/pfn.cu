@@ -144,13 +144,13 @@ __device__ __forceinline__ void store_scalar(const PfnArgs& a, int64_t idx, floa
     if (a.out_dtype == P3P_DTYPE_F32) {
         static_cast<float*>(a.out)[idx] = v;
     } else {
-        static_cast<unsigned short*>(a.out)[idx] = (unsigned short)(pack_bf16(v, 0.f) & 0xFFFF);
+        static_cast<unsigned short*>(a.out)[idx] = to_16bit(v, a.out_dtype);
     }
 }
 __device__ __forceinline__ int64_t out_index(const PfnArgs& a, int64_t item, int b, int cell, int c) {
     if (a.item_mode == kItemsCanvas && a.out_layout == P3P_LAYOUT_NCHW)
         return ((int64_t)b * a.c_total + a.c_offset + c) * a.items_per_tile + cell;
-    return item * a.bl.C + c;
+    return item * a.row_stride + a.row_offset + c;
 }
 // one output value of item (b, cell): plain layouts, or the token sequence (row 1 + cell of the tile, + pos_embed)
 __device__ __forceinline__ void store_item(const PfnArgs& a, int64_t item, int b, int cell, int c, float v) {
@@ -335,11 +335,14 @@ __global__ void zero_lidar_kernel(PfnArgs a) {
     const int C = a.bl.C;
     const int64_t total = a.num_items * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t idx = i;
+        int64_t idx;
         if (a.out_layout == P3P_LAYOUT_NCHW) {
             const int64_t per_tile = (int64_t)C * a.items_per_tile;
             const int64_t b = i / per_tile, rem = i - b * per_tile;
             idx = (b * a.c_total + a.c_offset) * a.items_per_tile + rem;
+        } else {
+            const int64_t item = i / C;
+            idx = item * a.row_stride + a.row_offset + (i - item * C);
         }
         store_scalar(a, idx, 0.f);
     }
@@ -861,7 +864,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         const int g = (warp - kEpiWarp0) >> 2;
         const int quad = warp & 3;  // TMEM lanes this warp may read: 32 * (warp id % 4)
         const bool nchw = (kMode == 2) || (kMode == 0 && canvas && (a.out_layout == P3P_LAYOUT_NCHW));
-        const bool f32 = (kMode != 0) || (a.out_dtype == P3P_DTYPE_F32);
+        const bool f32 = (kMode == 2) || (kMode == 3) || (a.out_dtype == P3P_DTYPE_F32);  // (mode 1: rows of either width)
         const int C = a.bl.C, ipt = a.items_per_tile;
         // fast path: whole units inside one tile, every item exists -> no per-item bounds, two-cell vector stores
         const bool fast = (kMode != 0) || (canvas && (total_items % kUnit == 0) && (ipt % kUnit == 0) && a.token_rows == 0);
@@ -894,8 +897,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         const uint32_t valid_sa = opaque(smem_u32(sValid));
         const uint32_t taddr_o = opaque(taddr);
         // rows layout: this thread's channel of the unit's first cell; advanced by one pointer addition per unit
-        float* rows_dst = static_cast<float*>(a.out) + (int64_t)blockIdx.x * kUnit * C + c;
-        const int64_t rows_step = (int64_t)gridDim.x * kUnit * C;
+        const int64_t rs = a.row_stride;
+        const int64_t rows_first = (int64_t)blockIdx.x * kUnit * rs + a.row_offset + c;
+        float* rows_dst = static_cast<float*>(a.out) + rows_first;
+        unsigned short* rows_dst16 = static_cast<unsigned short*>(a.out) + rows_first;
+        const int64_t rows_step = (int64_t)gridDim.x * kUnit * rs;
         for (int j = 0; j < (g < MT ? my_units : 0); ++j) {
             const int ub = wu.b, ur = wu.r;  // tile / position of the unit's first item
             const int item0 = unit_item0;
@@ -978,18 +984,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                             dst[0] = make_float4(ob[0], ob[1], ob[2], ob[3]);
                             dst[1] = make_float4(ob[4], ob[5], ob[6], ob[7]);
                         } else {
+                            const int dt = a.out_dtype;
                             *reinterpret_cast<uint4*>(static_cast<unsigned short*>(a.out) + i0) =
-                                make_uint4(pack_bf16(ob[0], ob[1]), pack_bf16(ob[2], ob[3]), pack_bf16(ob[4], ob[5]), pack_bf16(ob[6], ob[7]));
+                                make_uint4((uint32_t)to_16bit(ob[0], dt) | ((uint32_t)to_16bit(ob[1], dt) << 16), (uint32_t)to_16bit(ob[2], dt) | ((uint32_t)to_16bit(ob[3], dt) << 16),
+                                           (uint32_t)to_16bit(ob[4], dt) | ((uint32_t)to_16bit(ob[5], dt) << 16), (uint32_t)to_16bit(ob[6], dt) | ((uint32_t)to_16bit(ob[7], dt) << 16));
                         }
                     } else if (f32) {
                         // (B, ny nx, C) rows: a warp writes 32 consecutive channels of each of the unit's 8 cells
                         float* dst = rows_dst;
 #pragma unroll
-                        for (int i = 0; i < kUnit; ++i) { *dst = ob[i]; dst += C; }
+                        for (int i = 0; i < kUnit; ++i) { *dst = ob[i]; dst += rs; }
                     } else {
-                        unsigned short* dst = static_cast<unsigned short*>(a.out) + (int64_t)item0 * C + c;
+                        // 16-bit rows (the channels-last input of the fusion convolution)
+                        unsigned short* dst = rows_dst16;
 #pragma unroll
-                        for (int i = 0; i < kUnit; ++i) dst[(int64_t)i * C] = (unsigned short)(pack_bf16(ob[i], 0.f) & 0xFFFF);
+                        for (int i = 0; i < kUnit; ++i) { *dst = to_16bit(ob[i], a.out_dtype); dst += rs; }
                     }
                 } else {
                     int bi = ub, ri = ur;
@@ -1004,7 +1013,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                                 static_cast<float*>(a.out)[((int64_t)bi * a.token_rows + 1 + ri) * C + c] =
                                     ob[i] + a.pos_embed[(int64_t)(1 + ri) * C + c];
                             } else {
-                                const int64_t idx = nchw ? ((int64_t)bi * a.c_total + a.c_offset + c) * ipt + ri : (int64_t)item * C + c;
+                                const int64_t idx = nchw ? ((int64_t)bi * a.c_total + a.c_offset + c) * ipt + ri : (int64_t)item * rs + a.row_offset + c;
                                 store_scalar(a, idx, ob[i]);
                             }
                         }
@@ -1013,6 +1022,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                 }
             }
             rows_dst += rows_step;
+            rows_dst16 += rows_step;
             if (quad == 0) PTL(9 + g, jn - 1, 3);
         }
     }
@@ -1033,12 +1043,9 @@ int launch_pfn_simt(const PfnArgs& a, cudaStream_t st) {
     if (a.num_items <= 0) return P3P_OK;
     if (a.num_items > 0x7fffffff - 64) return fail(P3P_ERR_UNSUPPORTED, "%lld work items exceed the 32-bit item index", (long long)a.num_items);
     const size_t smem = ((size_t)(a.g.M + 1) * kHStride + 256 + 32 + 96 + 32) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    // (the attribute belongs to the current device's context: set per launch, it is cheap)
+    P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const int sms = device_sm_count();
     const bool hoist = a.bl.C <= kSimtMaxThreads;
     const int threads = hoist ? (a.bl.C + 31) / 32 * 32 : kSimtMaxThreads;
@@ -1070,23 +1077,15 @@ int launch_zero_lidar(const PfnArgs& a, cudaStream_t st) {
 int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st) {
     if (a.num_items <= 0) return P3P_OK;
     if (a.num_items > 0x7fffffff - 64) return fail(P3P_ERR_UNSUPPORTED, "%lld work items exceed the 32-bit item index", (long long)a.num_items);
-    static bool attr_done = false;
-    if (!attr_done) {
-#define P3P_TC_ATTR(PREC, MODE)                                                                                         \
-    P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<PREC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)TcCfg<PREC>::kSmemBytes))
-        P3P_TC_ATTR(P3P_PRECISION_TF32, 0); P3P_TC_ATTR(P3P_PRECISION_TF32, 1); P3P_TC_ATTR(P3P_PRECISION_TF32, 2); P3P_TC_ATTR(P3P_PRECISION_TF32, 3);
-        P3P_TC_ATTR(P3P_PRECISION_BF16, 0); P3P_TC_ATTR(P3P_PRECISION_BF16, 1); P3P_TC_ATTR(P3P_PRECISION_BF16, 2); P3P_TC_ATTR(P3P_PRECISION_BF16, 3);
-        P3P_TC_ATTR(P3P_PRECISION_FP16, 0); P3P_TC_ATTR(P3P_PRECISION_FP16, 1); P3P_TC_ATTR(P3P_PRECISION_FP16, 2); P3P_TC_ATTR(P3P_PRECISION_FP16, 3);
-#undef P3P_TC_ATTR
-        attr_done = true;
-    }
     const int64_t units = (a.num_items + kUnit - 1) / kUnit;
     int64_t grid = device_sm_count();
     if (grid > units) grid = units;
     int mode = 0;
-    if (a.item_mode == kItemsCanvas && a.num_items % kUnit == 0 && a.items_per_tile % kUnit == 0 && a.out_dtype == P3P_DTYPE_F32)
-        mode = a.token_rows ? 3 : ((a.out_layout == P3P_LAYOUT_NCHW) ? 2 : 1);
+    if (a.item_mode == kItemsCanvas && a.num_items % kUnit == 0 && a.items_per_tile % kUnit == 0) {
+        if (a.token_rows) mode = a.out_dtype == P3P_DTYPE_F32 ? 3 : 0;
+        else if (a.out_layout == P3P_LAYOUT_NCHW) mode = a.out_dtype == P3P_DTYPE_F32 ? 2 : 0;
+        else mode = 1;  // rows, fp32 or 16-bit
+    }
     // Programmatic dependent launch: the CTAs start (TMEM allocation, barriers, weights -> shared memory) while the
     // voxelizer's last chunks drain, and wait for its results with griddepcontrol.wait before their first read.
     cudaLaunchAttribute attr[1];
@@ -1101,6 +1100,8 @@ int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st) {
 #define P3P_LAUNCH_TC(PREC, MODE)                      \
     do {                                               \
         cfg.dynamicSmemBytes = TcCfg<PREC>::kSmemBytes; \
+        P3P_CUDA_CHECK(cudaFuncSetAttribute(pfn_tc_kernel<PREC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)TcCfg<PREC>::kSmemBytes)); /* per device context: set per launch */ \
         P3P_CUDA_CHECK(cudaLaunchKernelEx(&cfg, pfn_tc_kernel<PREC, MODE>, a)); \
     } while (0)
 #define P3P_LAUNCH_TC_MODES(PREC)                         \

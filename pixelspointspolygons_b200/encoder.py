@@ -19,7 +19,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import P3P_DTYPE_BF16, P3P_DTYPE_F32, P3P_LAYOUT_NCHW, P3P_LAYOUT_NLC, P3P_PRECISION
+from ._lib import P3P_DTYPE_BF16, P3P_DTYPE_F16, P3P_DTYPE_F32, P3P_LAYOUT_NCHW, P3P_LAYOUT_NLC, P3P_PRECISION
 
 
 def _get(node, key, default=None):
@@ -34,6 +34,14 @@ def _get(node, key, default=None):
             return node[key]
         except Exception:
             return default
+
+
+def _out_dtype_code(out: torch.Tensor) -> int:
+    """Output element type of the kernels: fp32, bf16 or fp16 (anything else would be filled with the wrong bit patterns)."""
+    try:
+        return {torch.float32: P3P_DTYPE_F32, torch.bfloat16: P3P_DTYPE_BF16, torch.float16: P3P_DTYPE_F16}[out.dtype]
+    except KeyError:
+        raise TypeError(f"output buffer must be float32, bfloat16 or float16, got {out.dtype}") from None
 
 
 class PFNLayer(nn.Module):
@@ -231,10 +239,14 @@ class PointPillarsEncoder(nn.Module):
         device = values.device
         grid = self._grid()
         total = values.shape[0]
+        dt = _out_dtype_code(out)
+        hw = self.ny * self.nx
+        need = B * hw * (c_total if c_total > 0 else self.channels)
+        if out.device != device or not out.is_contiguous() or out.numel() < need:
+            raise ValueError(f"out must be a contiguous tensor of at least {need} elements on {device}")
         with torch.cuda.device(device):
             ws = self._workspace(grid, B, total, device)
             blob = self._blob(device, precision)
-            dt = P3P_DTYPE_F32 if out.dtype == torch.float32 else P3P_DTYPE_BF16
             rc = _lib.lib().p3p_encode(values.data_ptr(), values.shape[1], offsets.data_ptr(), B, total, C.byref(grid),
                                        blob.data_ptr(), self.channels, P3P_PRECISION[precision], out.data_ptr(), layout, dt,
                                        c_total, c_offset, int(lidar_zero), ws.data_ptr(), ws.numel(),
@@ -272,12 +284,16 @@ class PointPillarsEncoder(nn.Module):
     def forward(self, x_lidar, return_flattened: bool = True):
         if self.training:
             return self._forward_dense(x_lidar, return_flattened)
-        values, offsets, B = self._pack(x_lidar)
+        if isinstance(x_lidar, (list, tuple)):  # pack once (encode_into accepts the jagged pair as is)
+            values, offsets, B = self._pack(x_lidar)
+            x_lidar = torch.nested.nested_tensor_from_jagged(values, offsets)
+        B = x_lidar.shape[0]
+        device = x_lidar.values().device if x_lidar.is_nested else x_lidar.device
         hw = self.ny * self.nx
         if return_flattened:
-            out = torch.empty(B, hw, self.channels, dtype=self.out_dtype, device=values.device)
+            out = torch.empty(B, hw, self.channels, dtype=self.out_dtype, device=device)
             return self.encode_into(x_lidar, out, P3P_LAYOUT_NLC)
-        out = torch.empty(B, self.channels, self.ny, self.nx, dtype=self.out_dtype, device=values.device)
+        out = torch.empty(B, self.channels, self.ny, self.nx, dtype=self.out_dtype, device=device)
         return self.encode_into(x_lidar, out, P3P_LAYOUT_NCHW, c_total=self.channels, c_offset=0)
 
     # ------------------------------------------------------------------ parity / training surface

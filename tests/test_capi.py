@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     raw = C.CDLL(built_lib)
     for n in names:
         assert hasattr(raw, n), n
-    assert _lib.lib().p3p_version() == 100
+    assert _lib.lib().p3p_version() == 200
 
 
 def test_library_targets_sm_100a_with_tcgen05(built_lib):
@@ -39,6 +39,7 @@ def test_library_targets_sm_100a_with_tcgen05(built_lib):
     sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass or "UTCMMA" in sass or "UTC" in sass  # tcgen05.mma
     assert "LDTM" in sass                                          # tcgen05.ld
+    assert "UTMALDG" in sass                                       # TMA tensor loads (cp.async.bulk.tensor) of the convolution
     assert "FMNMX3" in sass                                        # 3-input max in the epilogue
 
 
@@ -63,5 +64,11 @@ def test_size_queries_and_argument_errors(built_lib):
     assert rc == -1 and b"point_stride" in l.p3p_last_error()
     with pytest.raises(_lib.P3PError):
         _lib.check(rc, "p3p_voxelize")
+    # the 3x3 convolution: blob size, operand type check, channel range check (before any CUDA call)
+    assert l.p3p_conv3x3_blob_bytes(768, 384) == 384 * 9 * 768 * 2 + 384 * 4
+    rc = l.p3p_conv3x3(None, 1, 28, 28, 768, None, 384, 3, 1, None, 1, 384, 0, None)
+    assert rc == -1
+    rc = l.p3p_patch_embed(None, 1, 3, 224, 224, 8, None, None, 384, 3, None, 0, 7, 384, 0, None)
+    assert rc == -1 and b"layout" in l.p3p_last_error()
     huge = _lib.make_grid((0, 0, 0), (2240, 2240, 100), (8, 8, 100), 64, 784, 280, 280)
     assert l.p3p_workspace_bytes(C.byref(huge), 1, 10) == 0 and b"ranking budget" in l.p3p_last_error()
