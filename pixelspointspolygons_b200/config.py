@@ -43,3 +43,56 @@ def default_cfg(device="cuda", in_size=224, voxel=(8, 8, 100), max_num_points_pe
         run_type=dict(logging=logging),
         experiment=dict(encoder=enc, lidar_dropout=lidar_dropout),
     ))
+
+
+def _resolve(root, path, value):
+    """OmegaConf-style relative interpolations `${.a}`, `${..a.b}` inside strings (what the reference's encoder yamls use)."""
+    import re
+
+    def lookup(m):
+        expr = m.group(1)
+        dots = len(expr) - len(expr.lstrip("."))
+        if dots == 0:
+            node, keys = root, expr.split(".")
+        else:
+            node, keys = root, path[:len(path) - dots]
+            for k in keys:
+                node = node[k]
+            keys = expr.lstrip(".").split(".")
+        for k in keys:
+            node = node[k]
+        return node
+
+    if not isinstance(value, str) or "${" not in value:
+        return value
+    whole = re.fullmatch(r"\$\{([^${}]+)\}", value)
+    if whole:
+        return _resolve(root, path, lookup(whole))
+    return re.sub(r"\$\{([^${}]+)\}", lambda m: str(_resolve(root, path, lookup(m))), value)
+
+
+def _resolve_tree(root, node=None, path=()):
+    node = root if node is None else node
+    for k, v in list(node.items()):
+        if isinstance(v, dict):
+            _resolve_tree(root, v, path + (k,))
+        else:
+            node[k] = _resolve(root, path + (k,), v)
+    return root
+
+
+def cfg_from_encoder_yaml(path, device="cuda", out_path=".", decoder_in_feature_dim=256, lidar_dropout=None, logging="WARNING",
+                          **encoder_overrides):
+    """The cfg object the reference composes with Hydra for one of its encoder yamls (R:config/encoder/*.yaml), built with
+    PyYAML alone: `cfg.experiment.encoder` = the file, with its relative `${...}` interpolations resolved against the
+    surrounding nodes the encoders read (`experiment.model.decoder.in_feature_dim`, `experiment.dataset.out_path`,
+    `host.device`, `run_type.logging`, `experiment.lidar_dropout`)."""
+    import yaml
+
+    with open(path) as f:
+        enc = yaml.safe_load(f)
+    enc.update(encoder_overrides)
+    tree = dict(host=dict(device=device), run_type=dict(logging=logging),
+                experiment=dict(encoder=enc, model=dict(decoder=dict(in_feature_dim=decoder_in_feature_dim)),
+                                dataset=dict(out_path=out_path), lidar_dropout=lidar_dropout))
+    return AttrDict.wrap(_resolve_tree(tree))

@@ -13,11 +13,11 @@
 // K = tap * Cin + ci; the BN shift and the conv bias become one fp32 vector.
 //
 // Kernel.  CTA = (image, strip of `rows` image rows) x all output channels: D[co, pos] with M = 128 channels per MMA tile
-// (up to 3 tiles side by side in TMEM), N = rows * W positions (a multiple of 16, <= 256).  K loop = 9 taps x Cin / 64
+// (up to 3 tiles side by side in TMEM, one issuing warp each), N = rows * W positions (a multiple of 16, <= 256).  K loop = 9 taps x Cin / 64
 // blocks of 64 channels (128-byte rows, SWIZZLE_128B): per block one 4-D TMA box (64 ch, W, rows, 1) of X shifted by the
 // tap -- the padding is the TMA's out-of-bounds zero fill, there is no im2col and no halo code -- and one 2-D box
-// (64, 128) of Wp per channel tile.  Warp 0 produces (TMA + mbarrier expect_tx), warp 1 issues tcgen05.mma and releases the
-// stages with tcgen05.commit, warps 2-5 drain TMEM: + shift, ReLU, store as token rows (B, H W, Cout) -- the
+// (64, 128) of Wp per channel tile.  Warp 0 produces (TMA + mbarrier expect_tx), warps 1-3 issue tcgen05.mma (one channel tile each) and
+// release the stages with tcgen05.commit, warps 4-7 drain TMEM: + shift, ReLU, store as token rows (B, H W, Cout) -- the
 // `.flatten(2).transpose(1, 2)` of the reference is the store address -- or NCHW.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -30,7 +30,7 @@ namespace p3p {
 
 namespace {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 256;  // warp 0: TMA producer, warps 1-3: one MMA issuer per channel tile, warps 4-7: epilogue
 constexpr int kKBlockBytes = 128;        // one operand row of a K block: 64 16-bit channels
 constexpr int kKBlock = 64;
 constexpr int kWTileBytes = 128 * kKBlockBytes;  // 128 output channels x 64 k
@@ -94,10 +94,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int iters = 9 * kblocks;
 
     if ((smem_u32(smem_dyn) & 1023u) != 0u) __trap();  // the swizzled operand tiles need 1024-byte alignment
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
-        for (int i = 0; i < a.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < a.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)a.co_tiles); }
+        mbar_init(acc_full, (uint32_t)a.co_tiles);
         fence_mbar_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
@@ -130,32 +130,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
-        const bool leader = elect_one();
-        const uint32_t idesc = make_idesc(a.fmt, 128, a.N);
-        const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, SWIZZLE_128B
-        int st = 0;
-        uint32_t use = 0;
-        for (int it = 0; it < iters; ++it) {
-            mbar_wait(&full[st], use & 1u);
-            tc_fence_after();
-            if (leader) {
-                const uint32_t s_lo = (smem_u32(stage0 + (size_t)st * a.stage_bytes) >> 4) | (1u << 16);
-                const uint32_t x_lo = s_lo + (uint32_t)((a.co_tiles * kWTileBytes) >> 4);
-                for (int t = 0; t < a.co_tiles; ++t) {
-                    const uint32_t w_lo = s_lo + (uint32_t)((t * kWTileBytes) >> 4);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc_mma<false>(tmem_base + (uint32_t)(t * a.acc_stride), ((uint64_t)desc_hi << 32) | (w_lo + (uint32_t)(k * 2)),
-                                      ((uint64_t)desc_hi << 32) | (x_lo + (uint32_t)(k * 2)), idesc, (it | k) != 0);
-                }
+    } else if (warp < 4) {
+        // =========================== MMA issuers: warp 1 + t owns channel tile t ===========================
+        // One elected thread per tile runs the whole loop (no per-iteration warp reconvergence): three issuing threads keep
+        // the tensor pipe's queue full, each stage is released when all of them have committed.
+        const int t = warp - 1;
+        if (t < a.co_tiles && elect_one()) {
+            const uint32_t idesc = make_idesc(a.fmt, 128, a.N);
+            const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;  // SBO = 1024 B, SWIZZLE_128B
+            const uint32_t d_tmem = tmem_base + (uint32_t)(t * a.acc_stride);
+            const uint32_t w_off = (uint32_t)((t * kWTileBytes) >> 4), x_off = (uint32_t)((a.co_tiles * kWTileBytes) >> 4);
+            const uint32_t stage16 = (uint32_t)(a.stage_bytes >> 4);
+            const uint32_t s0_lo = (smem_u32(stage0) >> 4) | (1u << 16);
+            int st = 0;
+            uint32_t use = 0, s_lo = s0_lo;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(&full[st], use & 1u);
+                tc_fence_after();
+                const uint64_t wd = desc_hi | (uint64_t)(s_lo + w_off), xd = desc_hi | (uint64_t)(s_lo + x_off);
+                tc_mma<false>(d_tmem, wd, xd, idesc, it != 0);
+                tc_mma<false>(d_tmem, wd + 2, xd + 2, idesc, 1);
+                tc_mma<false>(d_tmem, wd + 4, xd + 4, idesc, 1);
+                tc_mma<false>(d_tmem, wd + 6, xd + 6, idesc, 1);
                 tc_commit(&empty[st]);
-                if (it == iters - 1) tc_commit(acc_full);
+                s_lo += stage16;
+                if (++st == a.stages) { st = 0; ++use; s_lo = s0_lo; }
             }
-            __syncwarp();
-            if (++st == a.stages) { st = 0; ++use; }
+            tc_commit(acc_full);
         }
+        __syncwarp();
     } else {
         // =========================== epilogue: thread = output channel (TMEM lane), columns = positions ===================
         const int quad = warp & 3;
@@ -200,7 +203,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -344,6 +347,7 @@ int launch_conv3x3(const void* x, int B, int H, int W, int Cin, const void* blob
         return fail(P3P_ERR_UNSUPPORTED, "conv3x3 runs on 16-bit operands (precision bf16 or fp16), got %d", precision);
     if (Cin % kKBlock != 0) return fail(P3P_ERR_UNSUPPORTED, "conv3x3 needs in_channels a multiple of %d, got %d", kKBlock, Cin);
     const int co_tiles = (Cout + 127) / 128;
+    if (co_tiles > 3) return fail(P3P_ERR_UNSUPPORTED, "conv3x3 supports up to 384 output channels (one issuing warp per 128), got %d", Cout);
     // strip height: rows * W a multiple of 16, <= 256, co_tiles accumulators of rows * W columns inside the 512 TMEM columns,
     // box dimensions <= 256; the tallest strip wins (weight tiles are re-read per strip)
     if (W > 256) return fail(P3P_ERR_UNSUPPORTED, "conv3x3 supports widths up to 256, got %d", W);

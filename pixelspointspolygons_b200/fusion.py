@@ -238,17 +238,19 @@ class EarlyFusionFrontEnd(nn.Module):
         self.fusion_layer = ConvBnRelu3x3(2 * dim, dim, precision=self.lidar_embed.precision)
         self._side_streams = {}
 
-    def _dropout_now(self) -> bool:
-        """early_fusion_vit.py:113-119 (one draw per forward, whole batch)."""
+    def _dropout_now(self, device=None) -> bool:
+        """early_fusion_vit.py:113-119: one draw per forward for the whole batch, `torch.rand(1, device=x_lidar.device)` --
+        i.e. from the generator of the LiDAR tensor's device, so that a seeded run drops the same batches as the reference
+        -- then `.item() <= p` (one host sync, as in the reference)."""
         p = _get(_get(self.cfg, "experiment"), "lidar_dropout", None)
         if p is None:
             return False
-        return bool(torch.rand(1).item() <= float(p))
+        return bool(torch.rand(1, device=device).item() <= float(p))
 
     def forward_into(self, x_image, x_lidar, out: torch.Tensor, lidar_zero: Optional[bool] = None):
         """Eval-mode fused path: both halves written in place into `out` (B, 2C, ny, nx); returns `out`."""
         dim = self.channels
-        lidar_zero = self._dropout_now() if lidar_zero is None else bool(lidar_zero)
+        lidar_zero = self._dropout_now(out.device) if lidar_zero is None else bool(lidar_zero)
         # the two halves are independent until the concat: the patch embedding runs on a side stream next to the
         # voxelizer + PFN (fork / join by events, so a CUDA graph captures them as parallel branches)
         dev = out.device
@@ -280,8 +282,8 @@ class EarlyFusionFrontEnd(nn.Module):
     def forward_tokens_into(self, x_image, x_lidar, x16: torch.Tensor, out: torch.Tensor, lidar_zero: Optional[bool] = None):
         """forward_tokens with caller-owned buffers: x16 (B, ny, nx, 2C) 16-bit scratch, out (B, ny nx, C) fp32."""
         dim, le, fl = self.channels, self.lidar_embed, self.fusion_layer
-        lidar_zero = self._dropout_now() if lidar_zero is None else bool(lidar_zero)
         dev = x_image.device
+        lidar_zero = self._dropout_now(dev) if lidar_zero is None else bool(lidar_zero)
         cur = torch.cuda.current_stream(dev)
         side = self._side_streams.get(dev)
         if side is None:
@@ -297,7 +299,7 @@ class EarlyFusionFrontEnd(nn.Module):
         if self.training:  # BatchNorm batch statistics: the dense autograd route of the optional training step
             xi = self.image_embed(x_image)
             xl = self.lidar_embed(x_lidar, return_flattened=False)
-            if self._dropout_now():
+            if self._dropout_now(xl.device):
                 xl = xl * 0.0
             return torch.cat((xi, xl), dim=1)
         B = x_image.shape[0]

@@ -57,6 +57,16 @@ def edge_cases():
     rng = np.random.default_rng(42)
     blk = np.concatenate([pillar_block(4, 4, 700, 11), pillar_block(5, 4, 700, 12), pillar_block(4, 5, 30, 13)])
     c["stability_shuffled"] = ([blk[rng.permutation(len(blk))]], {})
+    # keys that cross M in a LATER ranking chunk of the tile (chunks are 1024 .. 4096 points): the kept set is the M lowest
+    # indices over chunk boundaries, whatever order the hardware serves the chunk's atomics in
+    filler = po.synth_tile(12000, 51)
+    filler = filler[(filler[:, 0] > 80) | (filler[:, 1] > 80)]  # keep cells (0..9, 0..9) free for the planted pillars
+    a_early, a_late = pillar_block(3, 3, 40, 14), pillar_block(3, 3, 100, 15)
+    b_early, b_late = pillar_block(4, 3, 63, 16), pillar_block(4, 3, 5, 17)
+    c_late = pillar_block(5, 3, 300, 18)  # 300 same-key points inside one chunk, far beyond M
+    k = len(filler) // 3
+    c["crossing_in_later_chunk"] = ([np.concatenate([a_early, b_early, filler[:k], a_late[:30], filler[k:2 * k], a_late[30:], b_late,
+                                                     c_late, filler[2 * k:]])], {})
     # B.9 extremes of the density ablation
     c["M4"] = ([po.synth_tile(3000, 21), po.synth_tile(100, 22)], dict(max_num_points=4))
     c["M512"] = ([po.synth_tile(30000, 23, clustered=True)], dict(max_num_points=512))
