@@ -377,7 +377,8 @@ constexpr int kPairsPerUnit = kUnit / 2;
 constexpr int kTiles = 3;                      // 128-channel MMA tiles (C <= 384)
 constexpr int kAccCols = 64;                   // TMEM columns of one accumulator stage: one pillar (64 operand rows)
 constexpr int kAccStages = 2;                  // accumulator stages per channel tile: the issuer refills one while the epilogue drains the other
-constexpr int kGCol0 = kTiles * kAccStages * kAccCols;  // first of the 3 x 16 columns holding W1b' hmax of a unit (384 + 16 m)
+constexpr int kGCol0 = kTiles * kAccStages * kAccCols;  // W1b' hmax of a unit: 2 slots (unit parity) x 3 tiles x 16 columns from 384 on
+constexpr int kGSlotCols = kTiles * 16;
 constexpr int kValidRing = 64;               // pairs of validity flags in flight between front end and epilogue (>= kNS + ring slack)
 constexpr int kStageRows = 128;                // operand rows of a pair: 2 x 64 slots
 
@@ -395,7 +396,7 @@ struct TcCfg {
     static constexpr int kNS = kTf32 ? P3P_NS_TF32 : P3P_NS_16;            // B-operand stages: pillar pairs in flight
     static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * kHStage + 2 * (size_t)kGStage;
     static constexpr size_t kSmemFloats = 10 * 32 + 384 + kNF * 128 * 4;
-    static constexpr size_t kSmemBytes = kSmemOperands + kSmemFloats * 4 + (2 * kNS + 2 * kTiles * kAccStages + 2 * kTiles + 2 + 2) * 8 + 16 + 2 * kNF * 4 + 2 * kValidRing + 4 * kEpiGroups * kUnit * 32 * 4;
+    static constexpr size_t kSmemBytes = kSmemOperands + kSmemFloats * 4 + (2 * kNS + 2 * kTiles * kAccStages + 4 * kTiles + 2 + 2) * 8 + 16 + 2 * kNF * 4 + 2 * kValidRing + 2 * 4 * kEpiGroups * kUnit * 32 * 4;
 };
 
 
@@ -504,13 +505,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     uint64_t* h_empty = bars + kNS;           // [kNS] MMA -> front end (one tcgen05.commit per channel tile)
     uint64_t* t_full = bars + 2 * kNS;                  // [3 tiles][2 stages] MMA warp m -> epilogue group m (tcgen05.commit), per pillar
     uint64_t* t_empty = t_full + kTiles * kAccStages;   // [3][2] epilogue group m -> MMA warp m (128 arrivals)
-    uint64_t* gt_full = t_empty + kTiles * kAccStages;  // [3] MMA warp m -> epilogue group m, per unit (W1b' hmax accumulator)
-    uint64_t* gt_empty = gt_full + kTiles;              // [3] epilogue group m -> MMA warp m (128 arrivals)
-    uint64_t* g_empty = gt_empty + kTiles;              // [2] MMA warps -> front end: hmax rows of the unit slot consumed (MT commits)
+    uint64_t* gt_full = t_empty + kTiles * kAccStages;  // [3 tiles][2 slots] MMA warp m -> epilogue group m, per unit (W1b' hmax accumulator)
+    uint64_t* gt_empty = gt_full + 2 * kTiles;          // [3][2] epilogue group m -> MMA warp m (128 arrivals)
+    uint64_t* g_empty = gt_empty + 2 * kTiles;          // [2] MMA warps -> front end: hmax rows of the unit slot consumed (MT commits)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_empty + 2);
     int* sDesc = reinterpret_cast<int*>(tmem_slot + 2);                 // [kNF][2] descriptor word of the item decoded next
     unsigned char* sValid = reinterpret_cast<unsigned char*>(sDesc + 2 * kNF);  // [kValidRing pairs][2]: the item holds a pillar
-    float* sRmax = reinterpret_cast<float*>(sValid + 2 * kValidRing);           // [12 epilogue warps][kUnit][32]: pillar maxima of the unit in work
+    float* sRmax = reinterpret_cast<float*>(sValid + 2 * kValidRing);           // [12 epilogue warps][2 unit parities][kUnit][32]: pillar maxima
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int MT = a.bl.MT;
@@ -526,7 +527,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     if (tid == 32) {
         for (int i = 0; i < kNS; ++i) { mbar_init(&h_full[i], 2); mbar_init(&h_empty[i], (uint32_t)MT); }
         for (int i = 0; i < kTiles * kAccStages; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
-        for (int i = 0; i < kTiles; ++i) { mbar_init(&gt_full[i], 1); mbar_init(&gt_empty[i], 128); }
+        for (int i = 0; i < 2 * kTiles; ++i) { mbar_init(&gt_full[i], 1); mbar_init(&gt_empty[i], 128); }
         mbar_init(&g_empty[0], (uint32_t)MT); mbar_init(&g_empty[1], (uint32_t)MT);
         fence_mbar_init();
     }
@@ -575,7 +576,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             const uint32_t a2_lo = ((smem_u32(sA2) + (uint32_t)(m * Cfg::kATile)) >> 4) | (1u << 16);
             const uint32_t h_lo = (smem_u32(sH) >> 4) | (1u << 16), g_lo = (smem_u32(sG) >> 4) | (1u << 16);
             const uint32_t d_tile = tmem_base + (uint32_t)(m * kAccStages * kAccCols);
-            const uint32_t d_g = tmem_base + (uint32_t)(kGCol0 + m * 16);
+            const uint32_t d_g = tmem_base + (uint32_t)(kGCol0 + m * 16);  // + kGSlotCols * (unit parity)
             uint64_t* tf = t_full + m * kAccStages;
             uint64_t* te = t_empty + m * kAccStages;
             int st = 0;
@@ -609,15 +610,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                 //      with one N = 16 MMA chain into the tile's 16 spare accumulator columns -----------------------------
                 if ((p & (kPairsPerUnit - 1)) == kPairsPerUnit - 1) {
                     const uint32_t j = (uint32_t)p / kPairsPerUnit, slot = j & 1u;
-                    mbar_wait(&gt_empty[m], (j & 1u) ^ 1u);
+                    mbar_wait(&gt_empty[m * 2 + slot], ((j >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     if (leader) {
                         const uint32_t gs_lo = g_lo + slot * (Cfg::kGStage >> 4);
 #pragma unroll
                         for (int k = 0; k < Cfg::kKSteps; ++k)
-                            tc_mma<kTf32>(d_g, ((uint64_t)desc_hi << 32) | (a2_lo + (uint32_t)(k * 2)),
+                            tc_mma<kTf32>(d_g + slot * kGSlotCols, ((uint64_t)desc_hi << 32) | (a2_lo + (uint32_t)(k * 2)),
                                           ((uint64_t)desc_hi << 32) | (gs_lo + (uint32_t)(k * 2)), idesc_g, k > 0);
-                        tc_commit(&gt_full[m]);
+                        tc_commit(&gt_full[m * 2 + slot]);
                         tc_commit(&g_empty[slot]);
                     }
                     __syncwarp();
@@ -884,7 +885,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         const uint32_t gaddr = tlane + (uint32_t)(kGCol0 + g * 16);
         const uint32_t tf_sa = opaque(smem_u32(t_full + g * kAccStages));   // stage s: + 8 s
         const uint32_t te_sa = opaque(smem_u32(t_empty + g * kAccStages));
-        const uint32_t gtf_sa = opaque(smem_u32(gt_full + g)), gte_sa = opaque(smem_u32(gt_empty + g));
+        const uint32_t gtf_sa = opaque(smem_u32(gt_full + 2 * g)), gte_sa = opaque(smem_u32(gt_empty + 2 * g));  // slot: + 8
         const int my_pillars = (g < MT) ? my_units * kUnit : 0;
         int jn = 0;
         // Pillar q of the CTA sits in accumulator stage q & 1 of the tile; its barrier phase is (q >> 1) & 1.  The probe of
@@ -893,7 +894,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         uint32_t ready = 0;
         bool inflight = false;  // the first 16 columns of the pillar in work are already on their way into va
         float va[16], vb[16];
-        const uint32_t rmax_sa = opaque(smem_u32(sRmax + (warp - kEpiWarp0) * (kUnit * 32) + lane));  // [kUnit][32 lanes] strip of this warp
+        const uint32_t rmax_sa = opaque(smem_u32(sRmax + (warp - kEpiWarp0) * (2 * kUnit * 32) + lane));  // [2][kUnit][32 lanes] strips of this warp
         const uint32_t valid_sa = opaque(smem_u32(sValid));
         const uint32_t taddr_o = opaque(taddr);
         // rows layout: this thread's channel of the unit's first cell; advanced by one pointer addition per unit
@@ -902,63 +903,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         float* rows_dst = static_cast<float*>(a.out) + rows_first;
         unsigned short* rows_dst16 = static_cast<unsigned short*>(a.out) + rows_first;
         const int64_t rows_step = (int64_t)gridDim.x * kUnit * rs;
-        for (int j = 0; j < (g < MT ? my_units : 0); ++j) {
-            const int ub = wu.b, ur = wu.r;  // tile / position of the unit's first item
-            const int item0 = unit_item0;
-            wu.step();
-            unit_item0 += (int)gridDim.x * kUnit;
-            // ---- the unit's 8 pillars: max over each pillar's 64 accumulator columns ---------------------------------
-            // (a rolled loop over the pairs: the register blocks of the loads keep one assignment; the pillar maxima wait
-            // for the unit's W1b' hmax term in a per-warp shared-memory strip, not in registers).  The loads form one
-            // pipeline across pillars: four loads of 16 columns per pillar through two register buffers, the arithmetic
-            // on one buffer overlapping the load into the other, and the first load of the NEXT pillar issued -- when its
-            // accumulator is already complete -- before the last maximum of the current one.
-#pragma unroll 1
-            for (int pr = 0; pr < kPairsPerUnit; ++pr) {
-#pragma unroll
-                for (int s = 0; s < kAccStages; ++s, ++jn) {
-                    const uint32_t tph = (uint32_t)(jn >> 1) & 1u;
-                    if (quad == 0) PTL(9 + g, jn, 0);
-                    if (!inflight) {
-                        if (!ready) mbar_wait_sa(tf_sa + 8u * s, tph);
-                        tc_fence_after();
-                        tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols), va);
-                    }
-                    if (quad == 0) PTL(9 + g, jn, 1);
-                    tmem_ld_wait16(va);
-                    tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 16), vb);
-                    ready = (jn + 1 < my_pillars) ? mbar_test_sa(tf_sa + 8u * (s ^ 1), (uint32_t)((jn + 1) >> 1) & 1u) : 0u;
-                    const float r0 = max16(va);
-                    tmem_ld_wait16(vb);
-                    tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 32), va);
-                    const float r1 = max16(vb);
-                    tmem_ld_wait16(va);
-                    tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 48), vb);
-                    const float r2 = max16(va);
-                    tmem_ld_wait16(vb);
-                    tc_fence_before();
-                    mbar_arrive_sa(te_sa + 8u * s);
-                    // (the vote makes the decision warp-uniform: tcgen05.ld is a warp-wide instruction)
-                    inflight = __all_sync(0xffffffffu, ready != 0u) != 0;
-                    ready = inflight ? 1u : 0u;
-                    if (inflight) {
-                        tc_fence_after();
-                        tmem_ld16_issue(taddr_o + (uint32_t)((s ^ 1) * kAccCols), va);
-                    }
-                    sts_f32(rmax_sa + (uint32_t)((2 * pr + s) * 128), fmaxf(fmax3(r0, r1, r2), max16(vb)));
-                    if (quad == 0) PTL(9 + g, jn, 2);
-                }
-            }
+        // ---- W1b' hmax of the unit's 8 items (one MMA per unit), bias, relu, the 8 cells --------------------------------
+        auto unit_tail = [&](int j, int ub, int ur, int item0) {
             float rmax[kUnit];
 #pragma unroll
-            for (int i = 0; i < kUnit; ++i) rmax[i] = lds_f32(rmax_sa + (uint32_t)(i * 128));
+            for (int i = 0; i < kUnit; ++i) rmax[i] = lds_f32(rmax_sa + (uint32_t)((j & 1) * (kUnit * 128) + i * 128));
             // ---- W1b' hmax of the unit's 8 items (one MMA per unit), bias, relu, the 8 cells ---------------------------
             float gv[8];
-            mbar_wait_sa(gtf_sa, (uint32_t)j & 1u);
+            mbar_wait_sa(gtf_sa + 8u * ((uint32_t)j & 1u), ((uint32_t)j >> 1) & 1u);
             tc_fence_after();
-            tmem_ld8_wait(gaddr, gv);
+            tmem_ld8_wait(gaddr + (uint32_t)((j & 1) * kGSlotCols), gv);
             tc_fence_before();
-            mbar_arrive_sa(gte_sa);
+            mbar_arrive_sa(gte_sa + 8u * ((uint32_t)j & 1u));
             // which items hold a pillar: written by the front end before the pairs' operands were released
             const uint2 vv = lds_u32x2(valid_sa + (uint32_t)(((j * kPairsPerUnit) & (kValidRing - 1)) * 2));
             float ob[kUnit];
@@ -1023,8 +979,63 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             }
             rows_dst += rows_step;
             rows_dst16 += rows_step;
-            if (quad == 0) PTL(9 + g, jn - 1, 3);
+            if (quad == 0) PTL(9 + g, 8 * j + 7, 3);
+        };
+        int prev_ub = 0, prev_ur = 0, prev_item0 = 0;
+        const int my_units_g = (g < MT) ? my_units : 0;
+        for (int j = 0; j < my_units_g; ++j) {
+            const int ub = wu.b, ur = wu.r;  // tile / position of the unit's first item
+            const int item0 = unit_item0;
+            wu.step();
+            unit_item0 += (int)gridDim.x * kUnit;
+            // ---- the unit's 8 pillars: max over each pillar's 64 accumulator columns ---------------------------------
+            // (a rolled loop over the pairs: the register blocks of the loads keep one assignment; the pillar maxima wait
+            // for the unit's W1b' hmax term in a per-warp shared-memory strip, not in registers).  The loads form one
+            // pipeline across pillars: four loads of 16 columns per pillar through two register buffers, the arithmetic
+            // on one buffer overlapping the load into the other, and the first load of the NEXT pillar issued -- when its
+            // accumulator is already complete -- before the last maximum of the current one.
+#pragma unroll 1
+            for (int pr = 0; pr < kPairsPerUnit; ++pr) {
+#pragma unroll
+                for (int s = 0; s < kAccStages; ++s, ++jn) {
+                    const uint32_t tph = (uint32_t)(jn >> 1) & 1u;
+                    if (quad == 0) PTL(9 + g, jn, 0);
+                    if (!inflight) {
+                        if (!ready) mbar_wait_sa(tf_sa + 8u * s, tph);
+                        tc_fence_after();
+                        tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols), va);
+                    }
+                    if (quad == 0) PTL(9 + g, jn, 1);
+                    tmem_ld_wait16(va);
+                    tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 16), vb);
+                    ready = (jn + 1 < my_pillars) ? mbar_test_sa(tf_sa + 8u * (s ^ 1), (uint32_t)((jn + 1) >> 1) & 1u) : 0u;
+                    const float r0 = max16(va);
+                    tmem_ld_wait16(vb);
+                    tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 32), va);
+                    const float r1 = max16(vb);
+                    tmem_ld_wait16(va);
+                    tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 48), vb);
+                    const float r2 = max16(va);
+                    tmem_ld_wait16(vb);
+                    tc_fence_before();
+                    mbar_arrive_sa(te_sa + 8u * s);
+                    // (the vote makes the decision warp-uniform: tcgen05.ld is a warp-wide instruction)
+                    inflight = __all_sync(0xffffffffu, ready != 0u) != 0;
+                    ready = inflight ? 1u : 0u;
+                    if (inflight) {
+                        tc_fence_after();
+                        tmem_ld16_issue(taddr_o + (uint32_t)((s ^ 1) * kAccCols), va);
+                    }
+                    sts_f32(rmax_sa + (uint32_t)((j & 1) * (kUnit * 128) + (2 * pr + s) * 128), fmaxf(fmax3(r0, r1, r2), max16(vb)));
+                    if (quad == 0) PTL(9 + g, jn, 2);
+                }
+                // the PREVIOUS unit's tail runs here, after this unit's first pair: both accumulator stages have just been
+                // handed back, so the issuer refills them while this group adds the W1b' hmax term and stores
+                if (pr == 0 && j > 0) unit_tail(j - 1, prev_ub, prev_ur, prev_item0);
+            }
+            prev_ub = ub; prev_ur = ur; prev_item0 = item0;
         }
+        if (my_units_g > 0) unit_tail(my_units_g - 1, prev_ub, prev_ur, prev_item0);
     }
     tc_fence_before();
     __syncthreads();

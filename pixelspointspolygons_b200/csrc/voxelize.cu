@@ -110,18 +110,60 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Executed by warp 0: map ticket -> (tile, local chunk).  Tiles are walked 32 at a time.  The chunks of a tile start at
-// its first point rounded down to an index = phase (mod 4), the indices at which the packed xyz array is 16-byte aligned
-// (address = base + 12 * index; phase = (base / 4) mod 4).
+// Executed by warp 0: map ticket -> (tile, local chunk).  The chunks of a tile start at its first point rounded down to
+// an index = phase (mod 4), the indices at which the packed xyz array is 16-byte aligned (address = base + 12 * index;
+// phase = (base / 4) mod 4).  Storage (flags, chunk rows) is tile-major: chunk c of tile b lives at gstart(b) + c.
+// Tickets are handed out CHUNK-major for batches of up to 32 tiles -- chunk 0 of every tile, then chunk 1 of every tile,
+// ... -- so that in a multi-wave launch (dense tiles) the early chunks of all tiles run first and the later waves see
+// the tiles' saturation hints; a chunk still only waits for chunks with smaller tickets (its own tile's earlier ones).
 __device__ void locate_chunk(int g, const int64_t* __restrict__ offsets, int B, int S, int phase, ChunkLoc* out) {
     const int lane = threadIdx.x & 31;
+    if (B <= 32) {
+        long long o0 = 0, o1 = 0;
+        if (lane < B) { o0 = offsets[lane]; o1 = offsets[lane + 1]; }
+        const long long a0 = o0 - ((o0 - phase) & 3ll);  // largest index <= o0 that is = phase (mod 4)
+        const long long n = o1 > o0 ? o1 - a0 : 0;
+        const int nc = (int)((n + S - 1) / S);
+        int incl = nc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (g >= total) {
+            if (lane == 0) out->b = -1;
+            return;
+        }
+        // f(c) = sum_b min(nc_b, c) = tickets of chunk index < c; the ticket's chunk index is the largest c with f(c) <= g
+        int lo = 0, hi = __reduce_max_sync(0xffffffffu, nc) - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__reduce_add_sync(0xffffffffu, nc < mid ? nc : mid) <= g) lo = mid; else hi = mid - 1;
+        }
+        const int c = lo;
+        const int r = g - __reduce_add_sync(0xffffffffu, nc < c ? nc : c);  // rank among the tiles that have a chunk c
+        const bool has = nc > c;
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        if (has && __popc(bal & ((1u << lane) - 1u)) == r) {
+            out->b = lane;
+            out->c = c;
+            out->nchunks = nc;
+            out->gstart = incl - nc;
+            out->p0 = a0 + (long long)c * S;
+            out->lo = o0;
+            out->hi = o1;
+        }
+        return;
+    }
+    // more than 32 tiles: tile-major tickets, tiles walked 32 at a time
     int base = 0;
     bool found = false;
     for (int t0 = 0; t0 < B && !found; t0 += 32) {
         const int t = t0 + lane;
         long long o0 = 0, o1 = 0;
         if (t < B) { o0 = offsets[t]; o1 = offsets[t + 1]; }
-        const long long a0 = o0 - ((o0 - phase) & 3ll);  // largest index <= o0 that is = phase (mod 4)
+        const long long a0 = o0 - ((o0 - phase) & 3ll);
         const long long n = o1 > o0 ? o1 - a0 : 0;
         const int nc = (int)((n + S - 1) / S);
         int incl = nc;
@@ -443,12 +485,12 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
     // ---- publish this chunk's per-key counts (full rows: zeros beyond the keys in use) ------------------------------
     const int Kreg = (g.num_cells + 7) / 8 * 8 < Kp ? (g.num_cells + 7) / 8 * 8 : Kp;  // regular cells, 16-byte granular
     {
-        uint4* dst = reinterpret_cast<uint4*>(ws.chunk_hist + (size_t)ticket * Kp);
+        uint4* dst = reinterpret_cast<uint4*>(ws.chunk_hist + (size_t)(loc.gstart + loc.c) * Kp);
         for (int k8 = tid; k8 < Kp / 8; k8 += kThreads) dst[k8] = reinterpret_cast<const uint4*>(ctot_s)[k8];
         __syncthreads();  // every row store of the CTA happens before the release below (cumulativity)
         if (tid == 0) {
             __threadfence();
-            st_release(flags + ticket, 1u | ((unsigned)hi_key << 1));  // bit 0: published
+            st_release(flags + loc.gstart + loc.c, 1u | ((unsigned)hi_key << 1));  // bit 0: published
         }
         TL(blockIdx.x, 4);
         // wait for the earlier chunks of the tile; learn whether any of them holds keys beyond the regular cells
