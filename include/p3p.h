@@ -230,6 +230,17 @@ int p3p_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, cons
                       void* stream);
 
 /*
+ * The same front end fed with the packed transfer format (6 bytes per point instead of 12, halving the host -> device
+ * copy of a batch): per tile an int32 base (X0, Y0, Z0) and per point three uint16 deltas, X = X0 + dX etc.  -- what a
+ * loader gets from `las.X - las.X.min()` when the tile spans < 65536 steps of the LAS scale (56 m at 1 mm .. 1 cm).
+ * deltas: (total_points, 3) uint16; tile_base: (B, 3) int32.  Results are bit-identical to p3p_las_to_pixels on the same
+ * integers.
+ */
+int p3p_las_packed_to_pixels(const uint16_t* deltas, const int32_t* tile_base, const int64_t* tile_offsets, int32_t num_tiles,
+                             int64_t total_points, const p3p_las_tile* tiles, double z_hi, int32_t* minmax_ws, float* points,
+                             void* stream);
+
+/*
  * SURVEY 8f rank 1 -- the reference's `fusion_layer` (early_fusion_vit.py:75-79,123; early_fusion_vit_cnn.py:72-76,94):
  *     x = ReLU(BatchNorm2d(Conv2d(Cin, Cout, kernel_size=3, padding=1)(x)))        [ .flatten(2).transpose(1, 2) ]
  * as an implicit GEMM on the tensor cores.  The input is 16-bit channels-last, x: (B, H, W, Cin) fp16 (precision

@@ -5,7 +5,7 @@ Host side mirrors the reference's encoder plugin interface; the compute is libp3
 from .config import AttrDict, default_cfg  # noqa: F401
 from .encoder import PointPillarsEncoder  # noqa: F401
 from .fusion import ConvBnRelu3x3, EarlyFusionFrontEnd, PatchEmbed, ProjTail  # noqa: F401
-from .las import las_to_pixels  # noqa: F401
+from .las import LasPackedFrontEnd, las_packed_to_pixels, las_to_pixels, pack_las  # noqa: F401
 
 __all__ = ["AttrDict", "default_cfg", "PointPillarsEncoder", "EarlyFusionFrontEnd", "PatchEmbed", "ConvBnRelu3x3", "ProjTail",
-           "las_to_pixels"]
+           "las_to_pixels", "las_packed_to_pixels", "pack_las", "LasPackedFrontEnd"]

@@ -162,10 +162,9 @@ static int run_pfn(const PfnArgs& a, int precision, cudaStream_t st) {
     if (precision == P3P_PRECISION_FP32) return launch_pfn_simt(a, st);
     if (precision != P3P_PRECISION_TF32 && precision != P3P_PRECISION_BF16 && precision != P3P_PRECISION_FP16)
         return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
-    // The tensor-core kernel covers the shipped encoder configs and the low half of the density ablation (M <= 64: a
-    // pillar always takes 64 operand rows, C <= 384); M > 64 takes the exact-fp32 kernel, which is at least as accurate
-    // as either tensor-core contract.
-    if (a.g.M <= 64 && a.bl.MT <= 3 && a.g.fix2_scale > 0.f) return launch_pfn_tc(a, precision, st);
+    // The tensor-core kernel covers the shipped encoder configs and the density ablation (M <= 512: a pillar takes 1, 2, 4
+    // or 8 blocks of 64 operand rows; C <= 384); anything else takes the exact-fp32 kernel.
+    if (a.g.M <= 512 && a.bl.MT <= 3 && a.g.fix2_scale > 0.f) return launch_pfn_tc(a, precision, st);
     return launch_pfn_simt(a, st);
 }
 
@@ -368,8 +367,19 @@ int p3p_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, cons
     if (num_tiles == 0 || total_points == 0) return P3P_OK;
     if (!X || !Y || !Z || !tile_offsets || !tiles || !minmax_ws || !points) return fail(P3P_ERR_INVALID_ARGUMENT, "null pointer");
     if (!(z_hi > 0.0)) return fail(P3P_ERR_INVALID_ARGUMENT, "z_hi %g", z_hi);
-    return launch_las_to_pixels(X, Y, Z, tile_offsets, num_tiles, total_points, tiles, z_hi, minmax_ws, points,
+    return launch_las_to_pixels(X, Y, Z, nullptr, nullptr, tile_offsets, num_tiles, total_points, tiles, z_hi, minmax_ws, points,
                                 static_cast<cudaStream_t>(stream));
+}
+
+int p3p_las_packed_to_pixels(const uint16_t* deltas, const int32_t* tile_base, const int64_t* tile_offsets, int32_t num_tiles,
+                             int64_t total_points, const p3p_las_tile* tiles, double z_hi, int32_t* minmax_ws, float* points,
+                             void* stream) {
+    if (num_tiles < 0 || total_points < 0) return fail(P3P_ERR_INVALID_ARGUMENT, "negative batch or point count");
+    if (num_tiles == 0 || total_points == 0) return P3P_OK;
+    if (!deltas || !tile_base || !tile_offsets || !tiles || !minmax_ws || !points) return fail(P3P_ERR_INVALID_ARGUMENT, "null pointer");
+    if (!(z_hi > 0.0)) return fail(P3P_ERR_INVALID_ARGUMENT, "z_hi %g", z_hi);
+    return launch_las_to_pixels(nullptr, nullptr, nullptr, deltas, tile_base, tile_offsets, num_tiles, total_points, tiles, z_hi,
+                                minmax_ws, points, static_cast<cudaStream_t>(stream));
 }
 
 size_t p3p_conv3x3_blob_bytes(int32_t in_channels, int32_t out_channels) {

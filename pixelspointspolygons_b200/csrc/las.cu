@@ -35,15 +35,34 @@ __device__ __forceinline__ int tile_of(const int64_t* __restrict__ offsets, int 
     return lo;
 }
 
+// Where the raw integer coordinates of point i (tile b) come from: three int32 arrays (las.X / las.Y / las.Z), or the
+// packed transfer format -- per tile an int32 base and per point three uint16 deltas (6 bytes per point instead of 12: a
+// 56 m tile at the usual 1 mm .. 1 cm LAS scale spans < 65536 steps) -- which halves the host -> device copy.
+struct LasSource {
+    const int32_t* X;
+    const int32_t* Y;
+    const int32_t* Z;
+    const uint16_t* d;     // (total, 3) deltas, or NULL
+    const int32_t* base;   // (B, 3)
+    __device__ __forceinline__ void get(int64_t i, int b, int& x, int& y, int& z) const {
+        if (d) {
+            const uint16_t* p = d + i * 3;
+            x = base[b * 3 + 0] + (int)p[0]; y = base[b * 3 + 1] + (int)p[1]; z = base[b * 3 + 2] + (int)p[2];
+        } else {
+            x = X[i]; y = Y[i]; z = Z[i];
+        }
+    }
+};
+
 __global__ void __launch_bounds__(kLasThreads)
-las_minmax_kernel(const int32_t* __restrict__ X, const int32_t* __restrict__ Y, const int32_t* __restrict__ Z,
-                  const int64_t* __restrict__ offsets, int B, int64_t total, int32_t* mm) {
+las_minmax_kernel(LasSource src, const int64_t* __restrict__ offsets, int B, int64_t total, int32_t* mm) {
     for (int64_t i0 = (int64_t)blockIdx.x * kLasThreads; i0 < total; i0 += (int64_t)gridDim.x * kLasThreads) {
         const int64_t i = i0 + threadIdx.x;
         int b = -1, x = INT32_MAX, y = INT32_MAX, z0 = INT32_MAX, z1 = INT32_MIN;
         if (i < total) {
             b = tile_of(offsets, B, i);
-            x = X[i]; y = Y[i]; z0 = z1 = Z[i];
+            src.get(i, b, x, y, z0);
+            z1 = z0;
         }
         // a warp's 32 consecutive points mostly share a tile: reduce over the lanes of the first lane's tile, the
         // others (a tile boundary inside the warp) go straight to the atomics
@@ -63,15 +82,16 @@ las_minmax_kernel(const int32_t* __restrict__ X, const int32_t* __restrict__ Y, 
 }
 
 __global__ void __launch_bounds__(kLasThreads)
-las_pixels_kernel(const int32_t* __restrict__ X, const int32_t* __restrict__ Y, const int32_t* __restrict__ Z,
-                  const int64_t* __restrict__ offsets, int B, int64_t total, const p3p_las_tile* __restrict__ tiles,
+las_pixels_kernel(LasSource src, const int64_t* __restrict__ offsets, int B, int64_t total, const p3p_las_tile* __restrict__ tiles,
                   double z_hi, const int32_t* __restrict__ mm, float* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * kLasThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kLasThreads) {
         const int b = tile_of(offsets, B, i);
         const p3p_las_tile t = tiles[b];
-        const double x64 = __dadd_rn(__dmul_rn((double)X[i], t.scale[0]), t.offset[0]);
-        const double y64 = __dadd_rn(__dmul_rn((double)Y[i], t.scale[1]), t.offset[1]);
-        const double z64 = __dadd_rn(__dmul_rn((double)Z[i], t.scale[2]), t.offset[2]);
+        int Xi, Yi, Zi;
+        src.get(i, b, Xi, Yi, Zi);
+        const double x64 = __dadd_rn(__dmul_rn((double)Xi, t.scale[0]), t.offset[0]);
+        const double y64 = __dadd_rn(__dmul_rn((double)Yi, t.scale[1]), t.offset[1]);
+        const double z64 = __dadd_rn(__dmul_rn((double)Zi, t.scale[2]), t.offset[2]);
         double left = t.left, top = t.top;
         if (t.origin_from_min) {  // predictor.py:126: the tile's own minimum is the origin
             left = __dadd_rn(__dmul_rn((double)mm[b * 4 + 0], t.scale[0]), t.offset[0]);
@@ -115,17 +135,20 @@ las_pixels_kernel(const int32_t* __restrict__ X, const int32_t* __restrict__ Y, 
 
 }  // namespace
 
-int launch_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, const int64_t* offsets, int B, int64_t total,
-                         const p3p_las_tile* tiles, double z_hi, int32_t* mm, float* out, cudaStream_t st) {
+int launch_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, const uint16_t* deltas, const int32_t* base,
+                         const int64_t* offsets, int B, int64_t total, const p3p_las_tile* tiles, double z_hi, int32_t* mm, float* out,
+                         cudaStream_t st) {
     if (B <= 0 || total <= 0) return P3P_OK;
+    LasSource src;
+    src.X = X; src.Y = Y; src.Z = Z; src.d = deltas; src.base = base;
     las_init_kernel<<<(B * 4 + 127) / 128, 128, 0, st>>>(mm, B);
     P3P_CUDA_CHECK(cudaGetLastError());
     const int sms = device_sm_count();
     int64_t grid = (total + kLasThreads - 1) / kLasThreads;
     if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
-    las_minmax_kernel<<<(unsigned)grid, kLasThreads, 0, st>>>(X, Y, Z, offsets, B, total, mm);
+    las_minmax_kernel<<<(unsigned)grid, kLasThreads, 0, st>>>(src, offsets, B, total, mm);
     P3P_CUDA_CHECK(cudaGetLastError());
-    las_pixels_kernel<<<(unsigned)grid, kLasThreads, 0, st>>>(X, Y, Z, offsets, B, total, tiles, z_hi, mm, out);
+    las_pixels_kernel<<<(unsigned)grid, kLasThreads, 0, st>>>(src, offsets, B, total, tiles, z_hi, mm, out);
     P3P_CUDA_CHECK(cudaGetLastError());
     return P3P_OK;
 }

@@ -148,6 +148,7 @@ struct PfnArgs {
     int out_layout;  // P3P_LAYOUT_*
     int out_dtype;   // P3P_DTYPE_*
     int c_total, c_offset;
+    int blk_shift;               // tensor-core kernel, M > 64: log2 of the 64-row blocks per pillar (0: one block)
     int row_stride, row_offset;  // rows layouts: out[item * row_stride + row_offset + c] (row_stride = C when the rows are dense)
     // token sequence output (p3p_encode_tokens): rows of C channels, 1 + items_per_tile rows per tile, row 0 = class
     // token; pos_embed (1 + items_per_tile, C) is added to every row.  token_rows == 0: off
@@ -167,8 +168,9 @@ int launch_cls_rows(const PfnArgs& a, const float* cls_token, cudaStream_t st);
 int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, int P, const float* weight,
                        const float* bias, int C, int precision, void* out, int out_dtype, int out_layout, int c_total, int c_offset,
                        cudaStream_t st);
-int launch_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, const int64_t* offsets, int B, int64_t total,
-                         const p3p_las_tile* tiles, double z_hi, int32_t* mm, float* out, cudaStream_t st);
+int launch_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, const uint16_t* deltas, const int32_t* base,
+                         const int64_t* offsets, int B, int64_t total, const p3p_las_tile* tiles, double z_hi, int32_t* mm, float* out,
+                         cudaStream_t st);
 size_t conv3x3_blob_bytes(int Cin, int Cout);
 int launch_conv3x3_prepare(const p3p_conv_params* p, int precision, void* blob, cudaStream_t st);
 int launch_conv3x3(const void* x, int B, int H, int W, int Cin, const void* blob, int Cout, int precision, int relu, float* out,

@@ -369,8 +369,15 @@ constexpr int kRegMma = P3P_REG_MMA, kRegFront = P3P_REG_FRONT, kRegEpi = P3P_RE
 // setmaxnreg redistributes the CTA's OWN launch allocation (24 warps x 80 registers), not the SM's spare registers: a split
 // that exceeds it leaves the last warps spinning in the allocation forever
 static_assert(4 * kRegMma + 8 * kRegFront + 12 * kRegEpi <= 24 * 80, "register pool of the launch exceeded");
-#ifndef P3P_EPI_LD
-#define P3P_EPI_LD 16  // accumulator columns per tcgen05.ld of the epilogue (16: two 16-register buffers fit 72 registers)
+// Two epilogue schedules that were measured and did NOT pay (B = 16, fp16, kernel time): issuing the next pillar's first
+// load before the last maximum of the current one (P3P_EPI_PIPE: 41.9 -> 43.4 us) and running a unit's tail behind the
+// next unit's first pair (P3P_EPI_DEFER: -> 46.7 us; the accumulator stages are refilled during the tail either way).
+// Kept behind switches for the record; the double-buffered W1b'hmax accumulators / maxima strips they need stay.
+#ifndef P3P_EPI_PIPE
+#define P3P_EPI_PIPE 0
+#endif
+#ifndef P3P_EPI_DEFER
+#define P3P_EPI_DEFER 0
 #endif
 constexpr int kUnit = 8;                       // items per unit = 4 pillar pairs, consecutive canvas cells
 constexpr int kPairsPerUnit = kUnit / 2;
@@ -396,7 +403,7 @@ struct TcCfg {
     static constexpr int kNS = kTf32 ? P3P_NS_TF32 : P3P_NS_16;            // B-operand stages: pillar pairs in flight
     static constexpr size_t kSmemOperands = (size_t)6 * kATile + (size_t)kNS * kHStage + 2 * (size_t)kGStage;
     static constexpr size_t kSmemFloats = 10 * 32 + 384 + kNF * 128 * 4;
-    static constexpr size_t kSmemBytes = kSmemOperands + kSmemFloats * 4 + (2 * kNS + 2 * kTiles * kAccStages + 4 * kTiles + 2 + 2) * 8 + 16 + 2 * kNF * 4 + 2 * kValidRing + 2 * 4 * kEpiGroups * kUnit * 32 * 4;
+    static constexpr size_t kSmemBytes = kSmemOperands + kSmemFloats * 4 + (2 * kNS + 2 * kTiles * kAccStages + 4 * kTiles + 2 + 2) * 8 + 16 + 2 * kNF * 4 + 2 * kValidRing + 2 * 4 * kEpiGroups * kUnit * 32 * 4 + 2 * kNF * 4 * 4 + 2 * kNF * 32 * 4;
 };
 
 
@@ -512,11 +519,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
     int* sDesc = reinterpret_cast<int*>(tmem_slot + 2);                 // [kNF][2] descriptor word of the item decoded next
     unsigned char* sValid = reinterpret_cast<unsigned char*>(sDesc + 2 * kNF);  // [kValidRing pairs][2]: the item holds a pillar
     float* sRmax = reinterpret_cast<float*>(sValid + 2 * kValidRing);           // [12 epilogue warps][2 unit parities][kUnit][32]: pillar maxima
+    int* sBlkSum = reinterpret_cast<int*>(sRmax + 4 * kEpiGroups * 2 * kUnit * 32);  // [2 unit parities][kNF][4] fixed-point sums of a block
+    uint32_t* sBlkMax = reinterpret_cast<uint32_t*>(sBlkSum + 2 * kNF * 4);          // [2][kNF][32] hmax of a block (32 words: fp32, or 16 packed)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int MT = a.bl.MT;
     const int total_items = (int)a.num_items;
-    const int num_units = (total_items + kUnit - 1) / kUnit;
+    // M > 64 (density ablation, general mode only): a pillar = 2 / 4 / 8 consecutive 64-row blocks of a unit; its cluster
+    // mean and hmax are merged across the blocks' front-end warps, its maximum across the blocks in the epilogue
+    const int bs = (kMode == 0) ? a.blk_shift : 0;  // log2(blocks per pillar)
+    const int num_units = ((total_items << bs) + kUnit - 1) / kUnit;
     const int my_units = (num_units > (int)blockIdx.x) ? (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int my_pairs = my_units * kPairsPerUnit;  // pairs this CTA processes, in order p = 0, 1, ...
     const bool canvas = (kMode != 0) || (a.item_mode == kItemsCanvas);
@@ -660,7 +672,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         const uint32_t g_off0 = (uint32_t)fw * Cfg::RB + (uint32_t)(kTf32 ? (((2 * o) ^ (fw & 7)) * 16) : ((o ^ ((fw >> 1) & 3)) * 16));
         const uint32_t g_off1 = (uint32_t)fw * Cfg::RB + (uint32_t)(((2 * o + 1) ^ (fw & 7)) * 16);
         const float inv_nx = 1.0f / (float)a.g.nx;
-        auto item_of = [&](int j) -> int { return (j < my_units) ? ((int)blockIdx.x + j * (int)gridDim.x) * kUnit + fw : total_items; };
+        const int kblk = fw & ((1 << bs) - 1), row0 = kblk * 64;  // this warp's block of its pillar: slots [row0, row0 + 64)
+        auto item_of = [&](int j) -> int {
+            const int it = (((int)blockIdx.x + j * (int)gridDim.x) * kUnit + fw) >> bs;
+            return (j < my_units && it < total_items) ? it : total_items;
+        };
+        // rows of this warp's block that hold points, and whether the block takes part: it holds points, or it is the first
+        // empty block of a pillar with n < M whose blocks are all full (the padded slot of the reference lives there)
+        auto block_rows = [&](const Item& it) -> int {
+            const int r = it.n - row0;
+            return r < 0 ? 0 : (r > 64 ? 64 : r);
+        };
+        auto block_valid = [&](const Item& it) -> bool {
+            return it.valid && (bs == 0 || it.n > row0 || (it.n == row0 && it.n < a.g.M));
+        };
         // descriptor word of item j (canvas: cell_desc; list: resolved when decoded) travels through shared memory by
         // cp.async like the points, so no register waits on a global load
         int* my_desc = sDesc + 2 * fw;
@@ -673,7 +698,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             }
         };
         ItemWalk wk;  // position of the item decoded next
-        wk.init(item_of(0) < total_items ? item_of(0) : 0, (int)gridDim.x * kUnit, a.items_per_tile);
+        wk.init(item_of(0) < total_items ? item_of(0) : 0, ((int)gridDim.x * kUnit) >> bs, a.items_per_tile);
         auto decode = [&](int j, int d) -> Item {
             Item it;
             if (!canvas) {
@@ -690,11 +715,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             return it;
         };
         auto prefetch_points = [&](const Item& it, int set) {
-            if (it.valid) {
-                const float4* sl = item_slots(a, it);
+            if (block_valid(it)) {
+                const float4* sl = item_slots(a, it) + row0;
+                const int nr = block_rows(it);
                 const uint32_t dst = pbuf_sa + (uint32_t)set * 1024u + (uint32_t)lane * 16u;
-                cp_async16(dst, sl + lane, lane < it.n ? 16u : 0u);
-                cp_async16(dst + 512u, sl + lane + 32, lane + 32 < it.n ? 16u : 0u);
+                cp_async16(dst, sl + lane, lane < nr ? 16u : 0u);
+                cp_async16(dst + 512u, sl + lane + 32, lane + 32 < nr ? 16u : 0u);
             }
         };
         prefetch_desc(0);
@@ -720,19 +746,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             mbar_wait(&g_empty[j & 1], (((uint32_t)j >> 1) & 1u) ^ 1u);  // the unit slot's hmax rows of two units ago are consumed
             PTL(1 + fw, j, 1);
             const uint32_t gslot_sa = smem_u32(sG) + (uint32_t)(j & 1) * Cfg::kGStage;
-            if (it.valid) {
-                const int n = it.n;
-                const float4* P = pbuf + (j & 1) * 64;
-                // cluster mean on the fixed-point grid (exact integer sums: independent of the order of the slots);
-                // rows beyond n are zero-filled by the copy.  |q| * 64 slots < 2^31 (fix2_scale is sized for M).
+            const bool bvalid = block_valid(it);
+            const float4* P = pbuf + (j & 1) * 64;
+            uint32_t hm[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // M > 64: this block's hmax (8 fp32 channels, or 8 packed in 4 words)
+            // cluster mean on the fixed-point grid (exact integer sums: independent of the order of the slots); rows beyond
+            // the block's points are zero-filled by the copy.  |q| * M slots < 2^31 (fix2_scale is sized for M).
+            int sx = 0, sy = 0, sz = 0;
+            if (bvalid) {
+                const float4 s0 = P[lane], s1 = P[lane + 32];
+                const float fs = a.g.fix2_scale;
+                sx = __reduce_add_sync(0xffffffffu, __float2int_rn(s0.x * fs) + __float2int_rn(s1.x * fs));
+                sy = __reduce_add_sync(0xffffffffu, __float2int_rn(s0.y * fs) + __float2int_rn(s1.y * fs));
+                sz = __reduce_add_sync(0xffffffffu, __float2int_rn(s0.z * fs) + __float2int_rn(s1.z * fs));
+            }
+            if (bs) {  // the pillar's sums = the sums of its blocks (the blocks' warps meet at a named barrier)
+                int* mine = sBlkSum + ((j & 1) * kNF + fw) * 4;
+                if (lane == 0) { mine[0] = sx; mine[1] = sy; mine[2] = sz; }
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + (fw >> bs)), "r"(32 << bs) : "memory");
+                const int* first = sBlkSum + ((j & 1) * kNF + (fw - kblk)) * 4;
+                sx = sy = sz = 0;
+                for (int k = 0; k < (1 << bs); ++k) { sx += first[4 * k]; sy += first[4 * k + 1]; sz += first[4 * k + 2]; }
+            }
+            if (bvalid) {
+                const int n = block_rows(it);   // rows of this block that hold points
+                const int n_all = it.n;         // points of the pillar
                 float mpx, mpy, mz;
                 {
-                    const float4 s0 = P[lane], s1 = P[lane + 32];
-                    const float fs = a.g.fix2_scale;
-                    const int sx = __reduce_add_sync(0xffffffffu, __float2int_rn(s0.x * fs) + __float2int_rn(s1.x * fs));
-                    const int sy = __reduce_add_sync(0xffffffffu, __float2int_rn(s0.y * fs) + __float2int_rn(s1.y * fs));
-                    const int sz = __reduce_add_sync(0xffffffffu, __float2int_rn(s0.z * fs) + __float2int_rn(s1.z * fs));
-                    const float wn = __fdividef(a.g.fix2_inv, (float)n);
+                    const float wn = __fdividef(a.g.fix2_inv, (float)n_all);
                     mpx = (float)sx * wn - it.ctr_x;
                     mpy = (float)sy * wn - it.ctr_y;
                     mz = (float)sz * wn;
@@ -760,7 +800,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                     // rows beyond the pillar's n points: relu(BN(0)) of a padded slot while n < M; when the pillar is
                     // full at M < 64 the reference has no padded slot, the spare rows repeat slot 0 (the max ignores them)
                     float hp[8], mx8[8];
-                    if (n < a.g.M || n == 64) {
+                    if (n_all < a.g.M || n == 64) {
 #pragma unroll
                         for (int c = 0; c < 8; ++c) hp[c] = kc[9 * 32 + c];
                     } else {
@@ -797,7 +837,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
 #pragma unroll
                         for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(mx8[c], __shfl_xor_sync(0xffffffffu, mx8[c], off));
                     }
-                    if (pt == 0) {
+                    if (bs) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) hm[c] = __float_as_uint(mx8[c]);
+                    } else if (pt == 0) {
                         sts128(gslot_sa + g_off0, __float_as_uint(mx8[0]), __float_as_uint(mx8[1]), __float_as_uint(mx8[2]), __float_as_uint(mx8[3]));
                         sts128(gslot_sa + g_off1, __float_as_uint(mx8[4]), __float_as_uint(mx8[5]), __float_as_uint(mx8[6]), __float_as_uint(mx8[7]));
                     }
@@ -819,7 +862,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                         // rows beyond the pillar's n points: relu(BN(0)) of a padded slot while n < M; when the pillar
                         // is full at M < 64 the reference has no padded slot, the spare rows repeat slot 0
                         uint32_t hp[4];
-                        if (n < a.g.M) {
+                        if (n_all < a.g.M) {
 #pragma unroll
                             for (int c = 0; c < 4; ++c) hp[c] = pack_relu16<kPrec>(kc[9 * 32 + 2 * c], kc[9 * 32 + 2 * c + 1]);
                         } else {
@@ -849,10 +892,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) mm[c] = max16x2<kPrec>(mm[c], __shfl_xor_sync(0xffffffffu, mm[c], off));
                     }
-                    if (pt == 0) sts128(gslot_sa + g_off0, mm[0], mm[1], mm[2], mm[3]);
+                    if (bs) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) hm[c] = mm[c];
+                    } else if (pt == 0) {
+                        sts128(gslot_sa + g_off0, mm[0], mm[1], mm[2], mm[3]);
+                    }
                 }
             }
-            if (lane == 0) sValid[(p & (kValidRing - 1)) * 2 + half] = (unsigned char)it.valid;
+            if (bs) {
+                // hmax of the pillar = max over its blocks (h >= 0: an absent block contributes zeros); every block's warp
+                // writes the merged row as ITS hmax row of the unit, so the W1b' hmax MMA needs no notion of pillars
+                constexpr int kW = kTf32 ? 8 : 4;  // words per lane: 8 fp32 channels, or 8 channels packed in 4
+                uint32_t* mine = sBlkMax + ((j & 1) * kNF + fw) * 32 + kW * o;
+                if (pt == 0) {
+#pragma unroll
+                    for (int c = 0; c < kW; ++c) mine[c] = hm[c];
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + (fw >> bs)), "r"(32 << bs) : "memory");
+                if (pt == 0) {
+                    const uint32_t* first = sBlkMax + ((j & 1) * kNF + (fw - kblk)) * 32 + kW * o;
+                    for (int k = 0; k < (1 << bs); ++k) {
+#pragma unroll
+                        for (int c = 0; c < kW; ++c) {
+                            const uint32_t v = first[32 * k + c];
+                            if constexpr (kTf32) hm[c] = __float_as_uint(fmaxf(__uint_as_float(hm[c]), __uint_as_float(v)));
+                            else hm[c] = max16x2<kPrec>(hm[c], v);
+                        }
+                    }
+                    sts128(gslot_sa + g_off0, hm[0], hm[1], hm[2], hm[3]);
+                    if constexpr (kTf32) sts128(gslot_sa + g_off1, hm[4], hm[5], hm[6], hm[7]);
+                }
+            }
+            if (lane == 0) sValid[(p & (kValidRing - 1)) * 2 + half] = (unsigned char)bvalid;
             fence_async_smem();
             __syncwarp();
             PTL(1 + fw, j, 2);
@@ -868,7 +940,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
         const bool f32 = (kMode == 2) || (kMode == 3) || (a.out_dtype == P3P_DTYPE_F32);  // (mode 1: rows of either width)
         const int C = a.bl.C, ipt = a.items_per_tile;
         // fast path: whole units inside one tile, every item exists -> no per-item bounds, two-cell vector stores
-        const bool fast = (kMode != 0) || (canvas && (total_items % kUnit == 0) && (ipt % kUnit == 0) && a.token_rows == 0);
+        const bool fast = (kMode != 0) || (bs == 0 && canvas && (total_items % kUnit == 0) && (ipt % kUnit == 0) && a.token_rows == 0);
         const bool tokens = (kMode == 3);
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int cl = quad * 32 + lane;  // channel inside a 128-channel tile
@@ -876,8 +948,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
 #pragma unroll
         for (int mm = 0; mm < 3; ++mm) b1v[mm] = sB1[mm * 128 + cl];
         ItemWalk wu;  // position of the first item of the unit in work
-        wu.init((int)blockIdx.x * kUnit < total_items ? (int)blockIdx.x * kUnit : 0, (int)gridDim.x * kUnit, ipt);
-        int unit_item0 = (int)blockIdx.x * kUnit;
+        wu.init((((int)blockIdx.x * kUnit) >> bs) < total_items ? (((int)blockIdx.x * kUnit) >> bs) : 0, ((int)gridDim.x * kUnit) >> bs, ipt);
+        int unit_item0 = ((int)blockIdx.x * kUnit) >> bs;  // first pillar of the unit
         const int m = g;  // group g reads accumulator stage g = channel tile g
         const float bb = (m == 0) ? b1v[0] : ((m == 1) ? b1v[1] : b1v[2]);
         const int c = m * 128 + cl;
@@ -957,12 +1029,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                         for (int i = 0; i < kUnit; ++i) { *dst = to_16bit(ob[i], a.out_dtype); dst += rs; }
                     }
                 } else {
+                    if (bs) {
+                        // M > 64: the pillar's value = max over its blocks that took part (same W1b' hmax term in each)
+                        const int bpp = 1 << bs;
+#pragma unroll
+                        for (int i = 0; i < kUnit; ++i) {
+                            const unsigned word = i < 4 ? vv.x : vv.y;
+                            const bool v = ((word >> (8 * (i & 3))) & 0xFFu) != 0;
+                            ob[i] = v ? rmax[i] + (gv[i] + bb) : -INFINITY;
+                        }
+#pragma unroll
+                        for (int i = 0; i < kUnit; ++i) {
+                            if ((i & (bpp - 1)) == 0) {
+                                float mval = ob[i];
+#pragma unroll
+                                for (int k = 1; k < kUnit; ++k)
+                                    if (k < bpp && i + k < kUnit) mval = fmaxf(mval, ob[i + k]);
+                                ob[i >> bs] = mval == -INFINITY ? -INFINITY : fmaxf(mval, 0.f);  // (i >> bs <= i: no hazard)
+                            }
+                        }
+                    }
                     int bi = ub, ri = ur;
 #pragma unroll
                     for (int i = 0; i < kUnit; ++i) {
+                        if (bs && i >= (kUnit >> bs)) break;
                         const int item = item0 + i;
                         const unsigned word = i < 4 ? vv.x : vv.y;
-                        const bool v = ((word >> (8 * (i & 3))) & 0xFFu) != 0;
+                        bool v = ((word >> (8 * (i & 3))) & 0xFFu) != 0;
+                        if (bs) { v = ob[i] != -INFINITY; if (!v) ob[i] = 0.f; }
                         // list rows past num_pillars stay untouched, canvas cells are always written
                         if (item < total_items && (v || canvas)) {
                             if (a.token_rows) {  // token sequence: row 1 + cell of the tile, + pos_embed
@@ -987,13 +1081,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
             const int ub = wu.b, ur = wu.r;  // tile / position of the unit's first item
             const int item0 = unit_item0;
             wu.step();
-            unit_item0 += (int)gridDim.x * kUnit;
+            unit_item0 += ((int)gridDim.x * kUnit) >> bs;
             // ---- the unit's 8 pillars: max over each pillar's 64 accumulator columns ---------------------------------
             // (a rolled loop over the pairs: the register blocks of the loads keep one assignment; the pillar maxima wait
-            // for the unit's W1b' hmax term in a per-warp shared-memory strip, not in registers).  The loads form one
-            // pipeline across pillars: four loads of 16 columns per pillar through two register buffers, the arithmetic
-            // on one buffer overlapping the load into the other, and the first load of the NEXT pillar issued -- when its
-            // accumulator is already complete -- before the last maximum of the current one.
+            // for the unit's W1b' hmax term in a per-warp shared-memory strip, not in registers).  Four loads of 16
+            // columns per pillar through two register buffers: the arithmetic on one buffer overlaps the load into the
+            // other.
 #pragma unroll 1
             for (int pr = 0; pr < kPairsPerUnit; ++pr) {
 #pragma unroll
@@ -1020,22 +1113,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) pfn_tc_kernel(PfnArgs a) {
                     tc_fence_before();
                     mbar_arrive_sa(te_sa + 8u * s);
                     // (the vote makes the decision warp-uniform: tcgen05.ld is a warp-wide instruction)
+#if P3P_EPI_PIPE
                     inflight = __all_sync(0xffffffffu, ready != 0u) != 0;
                     ready = inflight ? 1u : 0u;
                     if (inflight) {
                         tc_fence_after();
                         tmem_ld16_issue(taddr_o + (uint32_t)((s ^ 1) * kAccCols), va);
                     }
+#endif
                     sts_f32(rmax_sa + (uint32_t)((j & 1) * (kUnit * 128) + (2 * pr + s) * 128), fmaxf(fmax3(r0, r1, r2), max16(vb)));
                     if (quad == 0) PTL(9 + g, jn, 2);
                 }
-                // the PREVIOUS unit's tail runs here, after this unit's first pair: both accumulator stages have just been
-                // handed back, so the issuer refills them while this group adds the W1b' hmax term and stores
+                // (P3P_EPI_DEFER: the PREVIOUS unit's tail runs here, after this unit's first pair)
+#if P3P_EPI_DEFER
                 if (pr == 0 && j > 0) unit_tail(j - 1, prev_ub, prev_ur, prev_item0);
+#endif
             }
+#if !P3P_EPI_DEFER
+            unit_tail(j, ub, ur, item0);
+#endif
             prev_ub = ub; prev_ur = ur; prev_item0 = item0;
         }
+#if P3P_EPI_DEFER
         if (my_units_g > 0) unit_tail(my_units_g - 1, prev_ub, prev_ur, prev_item0);
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -1085,14 +1186,18 @@ int launch_zero_lidar(const PfnArgs& a, cudaStream_t st) {
     return P3P_OK;
 }
 
-int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st) {
-    if (a.num_items <= 0) return P3P_OK;
-    if (a.num_items > 0x7fffffff - 64) return fail(P3P_ERR_UNSUPPORTED, "%lld work items exceed the 32-bit item index", (long long)a.num_items);
-    const int64_t units = (a.num_items + kUnit - 1) / kUnit;
+int launch_pfn_tc(const PfnArgs& a_in, int precision, cudaStream_t st) {
+    if (a_in.num_items <= 0) return P3P_OK;
+    if (a_in.num_items > 0x7fffffff - 64) return fail(P3P_ERR_UNSUPPORTED, "%lld work items exceed the 32-bit item index", (long long)a_in.num_items);
+    PfnArgs a = a_in;
+    a.blk_shift = 0;
+    while ((64 << a.blk_shift) < a.g.M) ++a.blk_shift;  // blocks per pillar: 1, 2, 4, 8
+    if ((a.num_items << a.blk_shift) > 0x7fffffff - 64) return fail(P3P_ERR_UNSUPPORTED, "too many row blocks for the 32-bit item index");
+    const int64_t units = ((a.num_items << a.blk_shift) + kUnit - 1) / kUnit;
     int64_t grid = device_sm_count();
     if (grid > units) grid = units;
     int mode = 0;
-    if (a.item_mode == kItemsCanvas && a.num_items % kUnit == 0 && a.items_per_tile % kUnit == 0) {
+    if (a.blk_shift == 0 && a.item_mode == kItemsCanvas && a.num_items % kUnit == 0 && a.items_per_tile % kUnit == 0) {
         if (a.token_rows) mode = a.out_dtype == P3P_DTYPE_F32 ? 3 : 0;
         else if (a.out_layout == P3P_LAYOUT_NCHW) mode = a.out_dtype == P3P_DTYPE_F32 ? 2 : 0;
         else mode = 1;  // rows, fp32 or 16-bit

@@ -131,7 +131,35 @@ def test_density_ablation_shapes(cuda_device, name):
     with torch.no_grad():
         rout = ref(tiles, return_flattened=True)
         out = enc(x, return_flattened=True)
-    assert_close(out, rout, 1e-3, name)
+        assert_close(out, rout, 1e-3, name)
+        # every precision and both layouts: M > 64 runs on the tensor cores as 2 / 4 / 8 blocks of 64 rows per pillar
+        rn = ref(tiles, return_flattened=False)
+        for prec, tol in (("tf32", 1e-3), ("bf16", 1e-2), ("fp32", 1e-4)):
+            o2 = enc.encode_into(x, torch.empty(len(tiles), 384, 28, 28, device=cuda_device), 0, c_total=384, c_offset=0, precision=prec)
+            torch.cuda.synchronize()
+            assert_close(o2, rn, tol, f"{name} {prec} nchw")
+        feats, coors = enc.pillar_features(x)
+        rv, rnum, rc, _ = ref.voxelize(tiles)
+        rf = ref.voxel_encoder(rv, rnum, rc)
+        assert_close(feats, rf, 1e-3, f"{name} pillar features")
+
+
+@pytest.mark.parametrize("M", [100, 128, 256])
+def test_pillars_around_block_boundaries(cuda_device, M):
+    """M > 64: pillars whose point counts sit on the 64-row block boundaries (63, 64, 65, 127, 128, 129, M - 1, M, M + 1, 1)
+    and a pillar beyond M -- the padded slot of the reference lives in a block of its own when n is a multiple of 64."""
+    counts = [63, 64, 65, 127, 128, 129, M - 1, M, M + 1, 1, 3 * M]
+    tile = np.concatenate([cases.pillar_block(2 * i % 28, 2 * (2 * i // 28), n, 70 + i) for i, n in enumerate(counts)])
+    tile = tile[np.random.default_rng(3).permutation(len(tile))]
+    grid = po.GridSpec(max_num_points=M)
+    enc, ref = build(cuda_device, grid, seed=6)
+    x = to_nested([tile], cuda_device)
+    with torch.no_grad():
+        rout = ref([tile], return_flattened=True)
+        for prec, tol in (("fp16", 1e-3), ("tf32", 1e-3), ("fp32", 1e-4)):
+            out = enc.encode_into(x, torch.empty(1, 784, 384, device=cuda_device), 1, precision=prec)
+            torch.cuda.synchronize()
+            assert_close(out, rout, tol, f"M={M} {prec}")
 
 
 def test_dense_input_equals_jagged(cuda_device):
@@ -351,6 +379,17 @@ def test_las_front_end_is_bit_exact(cuda_device, variant):
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), np.abs(got - ref).max()
     if variant == "dataset":
         assert got[:, :2].min() >= 0.0 and got[:, :2].max() <= 224.0
+    # the packed transfer format (uint16 deltas + int32 base per tile, 6 bytes per point): the same bits
+    from pixelspointspolygons_b200 import las_packed_to_pixels, pack_las
+
+    packed = [pack_las(X, Y, Z) for X, Y, Z in zip(Xs, Ys, Zs)]
+    deltas = torch.from_numpy(np.concatenate([d for d, _ in packed])).to(cuda_device)
+    base = torch.from_numpy(np.stack([b for _, b in packed])).to(cuda_device)
+    assert deltas.dtype == torch.uint16 and deltas.shape == (ref.shape[0], 3)
+    got16 = las_packed_to_pixels(deltas, base, offs, metas, z_hi=100.0, variant=variant).cpu().numpy()
+    assert np.array_equal(got16.view(np.uint32), ref.view(np.uint32))
+    with pytest.raises(ValueError, match="65535"):
+        pack_las(np.array([0, 70_000], np.int32), np.array([0, 1], np.int32), np.array([0, 1], np.int32))
 
 
 def test_las_front_end_d4_elements(cuda_device):
