@@ -582,80 +582,75 @@ def main():
 
     h2d = W.pinned_vals[0].numel() * 4 + W.pinned_offs.numel() * 8 + (W.pinned_img[0].numel() * 4 if fusion is not None else 0)
     e2e_value, e2e_steps = e2e_measure(False, min(1.0, args.min_seconds))
-    e2e_full_value, e2e_full_steps = e2e_measure(True, min(1.0, args.min_seconds))
 
-    # ---- the same loop fed with what a LAS file holds: integer coordinates, shipped as uint16 deltas + an int32 base per
-    #      tile (6 bytes per point over PCIe instead of 12); the loader arithmetic of p3_coco.py:74-101 (float64 scale /
-    #      offset, MinMaxScaler on z, clip) runs on the GPU (p3p_las_packed_to_pixels, bit-exact) in front of the encoder ----
-    from pixelspointspolygons_b200 import LasPackedFrontEnd
+    # ---- the serving loop of the package (HostPipeline): the loader's output is what a LAS file holds -- integer
+    #      coordinates as uint16 deltas + an int32 base per tile (6 bytes per point over PCIe instead of 12), the tile headers,
+    #      the fp32 image -- in pinned staging slots; per batch the host issues H2D(batch i + 1) on a copy stream, ONE CUDA-graph
+    #      launch compute(batch i) (‖ D2H(result i - 1) on a third stream).  The loader arithmetic of p3_coco.py:74-101 (float64 scale / offset, MinMaxScaler on z, clip)
+    #      runs on the GPU in front of the encoder, bit-exact (tests/test_gpu_parity.py, tests/test_gpu_pipeline.py) ----------
+    from pixelspointspolygons_b200 import HostPipeline
 
     las_sets = [synth_las_batch(t, None) for t in W.host_tiles]
-    pinned_d = [torch.from_numpy(d).pin_memory() for d, _, _ in las_sets]
-    pinned_b = [torch.from_numpy(b).pin_memory() for _, b, _ in las_sets]
-    las_fe = [LasPackedFrontEnd(las_sets[0][2], B * N, dev) for _ in range(nbuf)]  # (same headers for every set)
-    d_delta = [torch.empty(B * N, 3, dtype=torch.uint16, device=dev) for _ in range(nbuf)]
-    d_base = [torch.empty(B, 3, dtype=torch.int32, device=dev) for _ in range(nbuf)]
+    module = fusion if fusion is not None else enc
+    mode = "tokens" if args.workload == "fusion_layer" else "concat"
 
-    def las_copy(i):
-        s, b = i % nh, i % nbuf
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[b])
-            d_delta[b].copy_(pinned_d[s], non_blocking=True)
-            d_base[b].copy_(pinned_b[s], non_blocking=True)
-            d_offs[b].copy_(W.pinned_offs, non_blocking=True)
-            if fusion is not None:
-                d_img[b].copy_(W.pinned_img[s], non_blocking=True)
-            copied[b].record(copy_stream)
+    def pipeline_measure(host_result, seconds):
+        pipe = HostPipeline(module, B, B * N, slots=len(las_sets), mode=mode, host_result=host_result)
+        for i, (d, b, metas) in enumerate(las_sets):  # every slot holds its own batch: the timed loop re-sends them in turn
+            s = pipe.slots[i]
+            s.deltas.copy_(torch.from_numpy(d)); s.base.copy_(torch.from_numpy(b)); s.offsets.copy_(W.offs)
+            pipe.set_tiles(s, metas)
+            if s.image is not None:
+                s.image.copy_(W.pinned_img[i % len(W.pinned_img)])
 
-    def las_compute(i):
-        b = i % nbuf
-        main_stream.wait_event(copied[b])
-        vals = las_fe[b](d_delta[b], d_base[b], d_offs[b])
-        x = torch.nested.nested_tensor_from_jagged(vals, d_offs[b])
-        if args.workload == "fusion_layer":
-            y = fusion.forward_tokens(d_img[b], x, lidar_zero=False)
-        else:
-            y = fusion(d_img[b], x) if fusion is not None else enc(x, return_flattened=True)
-        consumed[b].record(main_stream)
-        h_sum[b].copy_(y.reshape(B, -1).sum(dim=1), non_blocking=True)
+        def run(n):
+            for _ in range(n):
+                pipe.staging()
+                pipe.submit()
 
-    def las_run(n):
-        las_copy(0)
-        for i in range(n):
-            if i + 1 < n:
-                las_copy(i + 1)
-            las_compute(i)
+        run(2 * pipe.n)
+        pipe.stream.synchronize()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n, tot = 0, 0.0
+        while tot < seconds * 1e3:
+            p0.record(pipe.stream)
+            run(64)
+            p1.record(pipe.stream)
+            p1.synchronize()
+            tot += p0.elapsed_time(p1)
+            n += 64
+        last = pipe.flush()
+        pipe.stream.synchronize()
+        check = float(last.out.float().abs().sum().item())
+        barrier()
+        m = torch.tensor([tot / n], device=dev)
+        if world > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        res = (B * world / (float(m.item()) * 1e-3), n, pipe.h2d_bytes_per_step, pipe.d2h_bytes_per_step, check)
+        del pipe
+        torch.cuda.empty_cache()
+        return res
 
-    for b in range(nbuf):
-        consumed[b].record(main_stream)
-    las_run(3)
-    barrier()
-    n_las, tot = 0, 0.0
-    while tot < min(1.0, args.min_seconds) * 1e3:
-        e0.record()
-        las_run(32)
-        e1.record()
-        e1.synchronize()
-        tot += e0.elapsed_time(e1)
-        n_las += 32
-    barrier()
-    m_las = torch.tensor([tot / n_las], device=dev)
-    if world > 1:
-        dist.all_reduce(m_las, op=dist.ReduceOp.MAX)
-    e2e_las_value = B * world / (float(m_las.item()) * 1e-3)
-    h2d_las = pinned_d[0].numel() * 2 + pinned_b[0].numel() * 4 + W.pinned_offs.numel() * 8 + (W.pinned_img[0].numel() * 4 if fusion is not None else 0)
-    e2e = {"value": e2e_las_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_las), "d2h_bytes_per_step": int(h_sum[0].numel() * 4),
-           "steps": n_las,
-           "input": "host-pinned LAS integer coordinates as uint16 deltas + int32 base per tile (6 B/point) + offsets (+ fp32 images); "
-                    "the reference loader's coordinate arithmetic runs on the GPU (p3p_las_packed_to_pixels) in front of the encoder",
+    e2e_las_value, n_las, h2d_las, d2h_las, chk = pipeline_measure(lambda y: y.reshape(B, -1).sum(dim=1), min(1.5, args.min_seconds))
+    e2e_full_value, e2e_full_steps, _, d2h_full, _ = pipeline_measure("full", min(1.0, args.min_seconds))
+    if not (chk > 0.0 and np.isfinite(chk)):
+        raise SystemExit("the pipeline's last result is empty or not finite")
+    e2e = {"value": e2e_las_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_las), "d2h_bytes_per_step": int(d2h_las),
+           "steps": n_las, "api": "pixelspointspolygons_b200.HostPipeline (staging() / submit() per batch)",
+           "input": "pinned host slots holding LAS integer coordinates as uint16 deltas + int32 base per tile (6 B/point), tile "
+                    "headers, offsets (+ fp32 images); the reference loader's coordinate arithmetic runs on the GPU "
+                    "(p3p_las_packed_to_pixels) in front of the encoder",
            "fp32_points_input": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "steps": e2e_steps,
-                                 "what": "the same loop fed with ready-made fp32 pixel-space points (12 B/point), as in round 1"},
+                                 "what": "eager module calls fed with ready-made fp32 pixel-space points (12 B/point), two device "
+                                         "buffers, H2D on a copy stream, as in round 1"},
            "host_numa": numa,
-           "result_read": "one float per tile (sum of the tile's output): the consumer of this path is the ViT on the same GPU, "
-                          "the host only needs a completion / sanity value",
-           "full_result_d2h": {"value": e2e_full_value, "unit": UNIT, "d2h_bytes_per_step": int(out_numel * 4), "steps": e2e_full_steps,
-                               "what": "the same loop copying the whole output tensor back to pinned host memory every step"},
-           "pipeline": "H2D of step i+1 on a copy stream overlaps the kernels of step i (2 device input buffers)"}
+           "result_read": "one float per tile (sum of the tile's output) copied to pinned memory inside every batch's graph: the "
+                          "consumer of this path is the ViT on the same GPU, the host only needs a completion / sanity value",
+           "full_result_d2h": {"value": e2e_full_value, "unit": UNIT, "d2h_bytes_per_step": int(d2h_full), "steps": e2e_full_steps,
+                               "what": "the same pipeline copying the whole output tensor of batch i - 1 back to pinned host memory "
+                                       "on a third stream"},
+           "pipeline": "per batch: H2D(i + 1) on the copy stream ‖ one CUDA-graph launch compute(i) ‖ D2H(i - 1) on the return stream"}
 
     # ---- per-kernel durations (CUDA events recorded inside p3p_encode on the launching stream) ----------------
     prof_steps = 100

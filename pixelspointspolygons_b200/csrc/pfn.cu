@@ -470,14 +470,6 @@ __device__ __forceinline__ float max16(const float (&v)[16]) {
     for (int i = 0; i < 5; ++i) r[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
     return fmax3(fmax3(r[0], r[1], r[2]), fmaxf(r[3], r[4]), v[15]);
 }
-__device__ __forceinline__ float max32(const float (&v)[32]) {
-    float r[11];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) r[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-    r[10] = fmaxf(v[30], v[31]);
-    return fmaxf(fmax3(fmax3(r[0], r[1], r[2]), fmax3(r[3], r[4], r[5]), fmax3(r[6], r[7], r[8])), fmaxf(r[9], r[10]));
-}
-
 // pfn_tc_kernel (M <= 64, C <= 384): per CTA a persistent pipeline
 //   8 front-end warps  : warp w takes item w of every unit (8 consecutive items); layer 0 in its affine form
 //                        W0' d_p + b0 = Ux x' + Uy y' + Uz z + kappa(pillar)   (x' = x - centre_x, ...)

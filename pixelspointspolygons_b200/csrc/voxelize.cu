@@ -69,25 +69,6 @@ struct ChunkLoc {
     unsigned sat;      // the tile's saturation word as read once for the whole CTA
 };
 
-// predicated 16-bit shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic, no branches)
-__device__ __forceinline__ unsigned lds_u16(uint32_t addr, int pred) {
-    unsigned v;
-    asm volatile(
-        "{\n .reg .pred p;\n .reg .b16 t;\n setp.ne.b32 p, %2, 0;\n mov.b16 t, 0;\n @p ld.shared.u16 t, [%1];\n cvt.u32.u16 %0, t;\n}"
-        : "=r"(v)
-        : "r"(addr), "r"(pred)
-        : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned lds_u32(uint32_t addr, int pred) {
-    unsigned v;
-    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n mov.b32 %0, 0;\n @p ld.shared.u32 %0, [%1];\n}"
-                 : "=r"(v)
-                 : "r"(addr), "r"(pred)
-                 : "memory");
-    return v;
-}
-
 // predicated atomic increment of a 16-bit shared-memory counter (through its 32-bit word; counters never overflow into
 // their neighbour); returns the counter's previous value
 __device__ __forceinline__ unsigned atoms_add_u16(uint32_t addr, int pred) {

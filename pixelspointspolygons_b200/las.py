@@ -16,8 +16,8 @@ import torch
 from . import _lib
 
 
-def _tile_meta(tiles: Sequence[dict], variant: str, dev) -> torch.Tensor:
-    """Per-tile constants (p3p_las_tile) as a device byte tensor."""
+def tile_meta_bytes(tiles: Sequence[dict], variant: str) -> bytes:
+    """Per-tile constants as the bytes of a p3p_las_tile array (what `HostPipeline.set_tiles` puts into a staging slot)."""
     if variant not in ("dataset", "predict"):
         raise ValueError("variant must be 'dataset' or 'predict'")
     arr = (_lib.LasTile * max(len(tiles), 1))()
@@ -42,7 +42,13 @@ def _tile_meta(tiles: Sequence[dict], variant: str, dev) -> torch.Tensor:
         e.d4 = _lib.P3P_D4[d4 if d4 is None else str(d4)]
         centre = t.get("center", (int(e.width) // 2, int(e.height) // 2))
         e.center_x, e.center_y = float(centre[0]), float(centre[1])
-    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+    return bytes(arr)[:C.sizeof(_lib.LasTile) * len(tiles)]
+
+
+def _tile_meta(tiles: Sequence[dict], variant: str, dev) -> torch.Tensor:
+    """Per-tile constants (p3p_las_tile) as a device byte tensor."""
+    raw = tile_meta_bytes(tiles, variant)
+    return torch.frombuffer(bytearray(raw if raw else b"\0" * C.sizeof(_lib.LasTile)), dtype=torch.uint8).to(dev)
 
 
 def las_to_pixels(X: torch.Tensor, Y: torch.Tensor, Z: torch.Tensor, offsets: torch.Tensor, tiles: Sequence[dict],
@@ -89,13 +95,15 @@ class LasPackedFrontEnd:
     """las_packed_to_pixels with everything that does not change between batches of one shape prepared once (tile
     constants on the device, scratch, output buffer): what a serving loop calls per batch, and what a CUDA graph can hold."""
 
-    def __init__(self, tiles: Sequence[dict], total: int, device, z_hi: float = 100.0, variant: str = "dataset"):
-        self.B, self.total, self.device, self.z_hi = len(tiles), int(total), device, float(z_hi)
-        self.meta = _tile_meta(tiles, variant, device)
+    def __init__(self, tiles: Sequence[dict], total: int, device, z_hi: float = 100.0, variant: str = "dataset", B: int = None):
+        # (B without tiles: the per-tile constants arrive with every call, `meta=` -- HostPipeline keeps them in its slots)
+        self.B, self.total, self.device, self.z_hi = (len(tiles) if B is None else int(B)), int(total), device, float(z_hi)
+        self.meta = _tile_meta(tiles, variant, device) if len(tiles) else None
         self.mm = torch.empty(4 * max(self.B, 1), dtype=torch.int32, device=device)
         self.out = torch.empty(self.total, 3, dtype=torch.float32, device=device)
 
-    def __call__(self, deltas: torch.Tensor, base: torch.Tensor, offsets: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    def __call__(self, deltas: torch.Tensor, base: torch.Tensor, offsets: torch.Tensor, out: torch.Tensor = None,
+                 meta: torch.Tensor = None) -> torch.Tensor:
         if deltas.dtype != torch.uint16 or base.dtype != torch.int32 or offsets.dtype != torch.int64:
             raise TypeError("deltas must be uint16 (N, 3), base int32 (B, 3), offsets int64")
         if not (deltas.is_cuda and base.is_cuda and offsets.is_cuda):
@@ -103,9 +111,12 @@ class LasPackedFrontEnd:
         if deltas.numel() != 3 * self.total or base.numel() != 3 * self.B or offsets.numel() != self.B + 1:
             raise ValueError("deltas / base / offsets sizes disagree with the prepared batch shape")
         out = self.out if out is None else out
+        meta = self.meta if meta is None else meta
+        if meta is None or not meta.is_cuda or meta.numel() * meta.element_size() < self.B * C.sizeof(_lib.LasTile):
+            raise ValueError("meta must be a CUDA byte tensor holding one p3p_las_tile per tile")
         with torch.cuda.device(self.device):
             rc = _lib.lib().p3p_las_packed_to_pixels(deltas.data_ptr(), base.data_ptr(), offsets.data_ptr(), self.B, self.total,
-                                                     self.meta.data_ptr(), C.c_double(self.z_hi), self.mm.data_ptr(), out.data_ptr(),
+                                                     meta.data_ptr(), C.c_double(self.z_hi), self.mm.data_ptr(), out.data_ptr(),
                                                      torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(rc, "p3p_las_packed_to_pixels")
         return out
