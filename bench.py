@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--precision", default="fp16", choices=["fp32", "tf32", "fp16", "bf16"])
     ap.add_argument("--max-points-per-voxel", type=int, default=64)
     ap.add_argument("--sets", type=int, default=8, help="rotating input/output sets (must exceed L2 in total)")
+    ap.add_argument("--in-flight", type=int, default=2, help="batches in flight: consecutive steps alternate between this many "
+                    "streams / workspaces (1 = every step waits for the previous one)")
     ap.add_argument("--no-graph", action="store_true", help="launch through the C ABI every step instead of CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub-results", action="store_true", help="skip the secondary configurations (tf32, fusion, density points)")
@@ -243,7 +245,7 @@ def workload_config(args):
             "fusion_layer": "Pix2Poly early fusion through fusion_layer (patch embed + LiDAR pillars + conv3x3 768->384 + BN + ReLU -> tokens)"}[args.workload]
     return {"workload": f"{name}, synthetic 224px tiles, {args.points} pts/tile, batch {args.batch} per GPU",
             "tiles_per_gpu": args.batch, "points_per_tile": args.points, "max_points_per_voxel": args.max_points_per_voxel,
-            "precision": args.precision,
+            "precision": args.precision, "in_flight": args.in_flight,
             "l2": f"rotating input+output sets per GPU (> 126 MB L2 in total; default {args.sets})",
             "parallelism": f"tiles sharded batch-wise over {args.gpus} GPU(s), no collective"}
 
@@ -304,11 +306,15 @@ class Workload:
     """One configuration of the hot path on this rank's GPU: modules, rotating input / output sets resident in HBM, and one
     CUDA graph per set (the steady-state serving loop replays them)."""
 
-    def __init__(self, dev, rank, workload, precision, B, N, M, sets, use_graph=True, keep_host=False):
+    def __init__(self, dev, rank, workload, precision, B, N, M, sets, use_graph=True, keep_host=False, lanes=2):
         from pixelspointspolygons_b200 import PointPillarsEncoder, _lib, default_cfg
         from tools import synth
 
         self.dev, self.workload, self.precision, self.B, self.N, self.M = dev, workload, precision, B, N, M
+        # batches in flight: consecutive steps alternate between `lanes` streams (one workspace each), so that the voxelizer
+        # of step i + 1 runs on the SMs the PFN of step i has not claimed yet / has already left
+        self.lanes = max(1, int(lanes))
+        self.streams = [torch.cuda.Stream(dev) for _ in range(self.lanes)]
         cfg = default_cfg(device=str(dev), max_num_points_per_voxel=M, p3p_precision=precision)
         self.enc = PointPillarsEncoder(cfg, voxel_encoder={"in_channels": 3, "feat_channels": [64, C_FEAT]},
                                        scatter={"in_channels": C_FEAT, "output_shape": [28, 28]}).to(dev).eval()
@@ -330,7 +336,8 @@ class Workload:
                 fl[1].running_var.copy_((torch.rand(C_FEAT, generator=g) + 0.5).to(dev))
         # enough rotating sets that consecutive uses of a set are > L2 apart
         per_set = 12 * N * B + (4 * 768 * HW * B + 4 * 3 * 224 * 224 * B if self.fusion is not None else 4 * C_FEAT * HW * B)
-        self.sets = sets = max(2, sets, -(-(160 << 20) // per_set))
+        sets = max(2, sets, -(-(160 << 20) // per_set))
+        self.sets = sets = -(-sets // self.lanes) * self.lanes  # a multiple of the lanes: set s always runs on lane s % lanes
         host_tiles = [[synth.synth_tile(N, 1000 * (1 + rank) + 16 * s + i, clustered=(i % 2 == 1)) for i in range(B)]
                       for s in range(min(sets, 8))]
         self.tiles0 = host_tiles[0]
@@ -361,51 +368,60 @@ class Workload:
         torch.cuda.synchronize()
         self.graphs = None
         if use_graph:
-            side = torch.cuda.Stream(dev)
             self.graphs = []
-            with torch.cuda.stream(side):
-                for s in range(sets):
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=side):
-                        self.step(s)
-                    self.graphs.append(g)
+            for s in range(sets):
+                st = self.streams[s % self.lanes]
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=st):
+                    self.step(s)
+                self.graphs.append(g)
             torch.cuda.synchronize()
 
-    def step(self, i):
+    def step(self, i, lane=None):
         s = i % self.sets
+        lane = s % self.lanes if lane is None else lane
         if self.workload == "fusion_layer":
-            self.fusion.forward_tokens_into(self.dev_img[s], self.dev_x[s], self.x16[s], self.outs[s], lidar_zero=False)
+            self.fusion.forward_tokens_into(self.dev_img[s], self.dev_x[s], self.x16[s], self.outs[s], lidar_zero=False, lane=lane)
         elif self.fusion is not None:
-            self.fusion.forward_into(self.dev_img[s], self.dev_x[s], self.outs[s])
+            self.fusion.forward_into(self.dev_img[s], self.dev_x[s], self.outs[s], lane=lane)
         else:
-            self.enc.encode_into(self.dev_x[s], self.outs[s], self._lib.P3P_LAYOUT_NLC)
+            self.enc.encode_into(self.dev_x[s], self.outs[s], self._lib.P3P_LAYOUT_NLC, lane=lane)
 
-    def run_step(self, i):
-        if self.graphs is not None:
-            self.graphs[i % self.sets].replay()
-        else:
-            self.step(i)
+    def run_step(self, i, single=False):
+        """Step i on its lane's stream (enqueue only); single: every step on ONE stream (a step starts when the previous ends)."""
+        s = i % self.sets
+        with torch.cuda.stream(self.streams[0 if single else s % self.lanes]):
+            if self.graphs is not None:
+                self.graphs[s].replay()
+            else:
+                self.step(i)
 
     @property
     def launches_per_step(self):
         # voxelize + PFN (+ patch embed (+ fusion convolution)); the counter memset is not a kernel
         return 2 if self.fusion is None else (4 if self.workload == "fusion_layer" else 3)
 
-    def time_steps(self, steps, first=0):
-        """Device time (ms) of `steps` back-to-back steps on the current stream."""
+    def time_steps(self, steps, first=0, single=False):
+        """Device time (ms) of `steps` steps issued back to back: the start event precedes the first step on every lane, the
+        end event follows the last step of every lane."""
+        cur = torch.cuda.current_stream(self.dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(cur)
+        for st in self.streams:
+            st.wait_event(e0)
         for i in range(steps):
-            self.run_step(first + i)
-        e1.record()
+            self.run_step(first + i, single)
+        for st in self.streams:
+            cur.wait_stream(st)
+        e1.record(cur)
         e1.synchronize()
         return e0.elapsed_time(e1)
 
-    def time_for(self, seconds, chunk=256):
+    def time_for(self, seconds, chunk=256, single=False):
         """Steps and device milliseconds of a loop of at least `seconds` (chunks of `chunk` steps between two events)."""
         total_ms, total_steps = 0.0, 0
         while total_ms < seconds * 1e3:
-            total_ms += self.time_steps(chunk, total_steps)
+            total_ms += self.time_steps(chunk, total_steps, single)
             total_steps += chunk
         return total_steps, total_ms
 
@@ -438,7 +454,8 @@ def sub_result(dev, rank, workload, precision, B, N, M, seconds=0.4):
         w.time_steps(20)
         steps, ms = w.time_for(seconds, chunk=64)
         out = {"workload": workload, "precision": precision, "tiles_per_gpu": B, "points_per_tile": N, "max_points_per_voxel": M,
-               "ms_per_step": ms / steps, "tiles_per_s_per_gpu": B * steps / (ms * 1e-3), "steps": steps, "sets": w.sets}
+               "ms_per_step": ms / steps, "tiles_per_s_per_gpu": B * steps / (ms * 1e-3), "steps": steps, "sets": w.sets,
+               "in_flight": w.lanes}
         if workload == "fusion_layer":
             peaks = {}
             try:
@@ -475,7 +492,8 @@ def main():
 
     numa = bind_to_gpu_numa(local_rank)
     B, N, M = args.batch, args.points, args.max_points_per_voxel
-    W = Workload(dev, rank, args.workload, args.precision, B, N, M, args.sets, use_graph=not args.no_graph, keep_host=True)
+    W = Workload(dev, rank, args.workload, args.precision, B, N, M, args.sets, use_graph=not args.no_graph, keep_host=True,
+                 lanes=args.in_flight)
     enc, fusion, sets = W.enc, W.fusion, W.sets
     flops, kept, pillars = algorithmic_flops(W.tiles0, M)
 
@@ -489,12 +507,9 @@ def main():
         W.run_step(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        W.run_step(i)
-    e1.record()
+    ms_region1 = W.time_steps(args.steps, first=args.warmup)
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ms = torch.tensor([ms_region1], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_k = float(ms.item())
@@ -511,6 +526,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item())
     value = B * world / (ms_per_step * 1e-3)
+    one_steps, one_ms = W.time_for(min(0.5, args.min_seconds), single=True)
+    t1 = torch.tensor([one_ms / one_steps], device=dev)
+    if world > 1:
+        dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+    one_in_flight = {"ms_per_step": float(t1.item()), "value": B * world / (float(t1.item()) * 1e-3), "unit": UNIT, "steps": one_steps,
+                     "what": "the same graphs replayed on ONE stream: a step starts when the previous one has ended (the latency-"
+                             "oriented number; `value` keeps `in_flight` batches in flight on as many streams / workspaces)"}
     burst = {"steps": args.steps, "ms_per_step": ms_k / args.steps, "value": B * world * args.steps / (ms_k * 1e-3), "unit": UNIT,
              "what": "exactly --steps steps between two events (short: boost clocks, no power limit)"}
 
@@ -657,7 +679,7 @@ def main():
     l = _lib.lib()
     _lib.check(l.p3p_profile_begin(prof_steps), "p3p_profile_begin")
     for i in range(prof_steps):
-        W.step(i)
+        W.step(i, lane=0)
     arr = [(C.c_float * prof_steps)() for _ in range(2)]
     cnt = C.c_int32(0)
     _lib.check(l.p3p_profile_end(arr[0], arr[1], prof_steps, C.byref(cnt)), "p3p_profile_end")
@@ -738,7 +760,7 @@ def main():
             "config": workload_config(args), "mpoints_per_s": value * N / 1e6,
             "timed_region": {"steps_timed": sus_steps, "seconds": sus_ms * 1e-3, "what": f"`value` / `ms_per_step`: the step loop held for >= {args.min_seconds} s "
                              "(max over ranks of the per-step time); `burst` is the contract's exactly-K-steps region"},
-            "burst": burst,
+            "burst": burst, "one_batch_in_flight": one_in_flight,
             "e2e": e2e, "gpu_launches": W.launches_per_step * (args.steps + sus_steps), "launch_mode": "cuda_graph" if W.graphs else "c_abi_per_step",
             "roofline": roofline, "hbm_roofline": hbm, "stage_ms": stage_ms, "sub_results": subs, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }

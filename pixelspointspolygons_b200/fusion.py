@@ -247,23 +247,28 @@ class EarlyFusionFrontEnd(nn.Module):
             return False
         return bool(torch.rand(1, device=device).item() <= float(p))
 
-    def forward_into(self, x_image, x_lidar, out: torch.Tensor, lidar_zero: Optional[bool] = None):
-        """Eval-mode fused path: both halves written in place into `out` (B, 2C, ny, nx); returns `out`."""
+    def forward_into(self, x_image, x_lidar, out: torch.Tensor, lidar_zero: Optional[bool] = None, lane: int = 0):
+        """Eval-mode fused path: both halves written in place into `out` (B, 2C, ny, nx); returns `out`.  `lane`: see
+        `PointPillarsEncoder.encode_into` (one lane per stream when several batches are in flight)."""
         dim = self.channels
         lidar_zero = self._dropout_now(out.device) if lidar_zero is None else bool(lidar_zero)
         # the two halves are independent until the concat: the patch embedding runs on a side stream next to the
         # voxelizer + PFN (fork / join by events, so a CUDA graph captures them as parallel branches)
         dev = out.device
         cur = torch.cuda.current_stream(dev)
-        side = self._side_streams.get(dev)
-        if side is None:
-            side = self._side_streams[dev] = torch.cuda.Stream(dev)
+        side = self._side_stream(dev, lane)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             self.image_embed.forward_into(x_image, out, 2 * dim, 0)
-        self.lidar_embed.encode_into(x_lidar, out, P3P_LAYOUT_NCHW, c_total=2 * dim, c_offset=dim, lidar_zero=lidar_zero)
+        self.lidar_embed.encode_into(x_lidar, out, P3P_LAYOUT_NCHW, c_total=2 * dim, c_offset=dim, lidar_zero=lidar_zero, lane=lane)
         cur.wait_stream(side)
         return out
+
+    def _side_stream(self, dev, lane: int = 0):
+        side = self._side_streams.get((dev, lane))
+        if side is None:
+            side = self._side_streams[(dev, lane)] = torch.cuda.Stream(dev)
+        return side
 
     def forward_tokens(self, x_image, x_lidar, lidar_zero: Optional[bool] = None) -> torch.Tensor:
         """`EarlyFusionViT.forward` through `self.fusion_layer(x).flatten(2).transpose(1, 2)` (early_fusion_vit.py:96-123):
@@ -279,19 +284,18 @@ class EarlyFusionFrontEnd(nn.Module):
         out = torch.empty(B, le.ny * le.nx, dim, dtype=torch.float32, device=dev)
         return self.forward_tokens_into(x_image, x_lidar, x16, out, lidar_zero)
 
-    def forward_tokens_into(self, x_image, x_lidar, x16: torch.Tensor, out: torch.Tensor, lidar_zero: Optional[bool] = None):
+    def forward_tokens_into(self, x_image, x_lidar, x16: torch.Tensor, out: torch.Tensor, lidar_zero: Optional[bool] = None,
+                            lane: int = 0):
         """forward_tokens with caller-owned buffers: x16 (B, ny, nx, 2C) 16-bit scratch, out (B, ny nx, C) fp32."""
         dim, le, fl = self.channels, self.lidar_embed, self.fusion_layer
         dev = x_image.device
         lidar_zero = self._dropout_now(dev) if lidar_zero is None else bool(lidar_zero)
         cur = torch.cuda.current_stream(dev)
-        side = self._side_streams.get(dev)
-        if side is None:
-            side = self._side_streams[dev] = torch.cuda.Stream(dev)
+        side = self._side_stream(dev, lane)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             self.image_embed.forward_into(x_image, x16, 2 * dim, 0, layout=P3P_LAYOUT_NLC)
-        le.encode_into(x_lidar, x16, P3P_LAYOUT_NLC, c_total=2 * dim, c_offset=dim, lidar_zero=lidar_zero)
+        le.encode_into(x_lidar, x16, P3P_LAYOUT_NLC, c_total=2 * dim, c_offset=dim, lidar_zero=lidar_zero, lane=lane)
         cur.wait_stream(side)
         return fl.forward_nhwc(x16, out, P3P_LAYOUT_NLC)
 

@@ -126,3 +126,23 @@ def test_pipeline_refuses_cpu_modules_and_train_mode(cuda_device):
     enc.eval()
     with pytest.raises(RuntimeError, match="CUDA"):
         HostPipeline(enc.cpu(), B, TOTAL)
+
+
+def test_batches_in_flight_on_two_lanes_equal_the_serial_result(cuda_device):
+    """Two streams, two workspaces (`lane`): many alternating calls with different batches, every output equal to the one
+    a plain single-stream call gives."""
+    from pixelspointspolygons_b200._lib import P3P_LAYOUT_NLC
+
+    cfg, enc, _, _ = encoder(cuda_device)
+    xs = [direct_points(las_batch(30 + s), cuda_device) for s in range(6)]
+    want = [enc(x, return_flattened=True).clone() for x in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(cuda_device), torch.cuda.Stream(cuda_device)]
+    outs = [torch.empty_like(w) for w in want]
+    for rep in range(4):
+        for i, x in enumerate(xs):
+            with torch.cuda.stream(streams[i % 2]):
+                enc.encode_into(x, outs[i], P3P_LAYOUT_NLC, lane=i % 2)
+    torch.cuda.synchronize()
+    for o, w in zip(outs, want):
+        assert torch.equal(o, w)
