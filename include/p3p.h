@@ -218,6 +218,22 @@ int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, in
                     void* out, int32_t out_dtype, int32_t out_layout, int32_t c_total, int32_t c_offset, void* stream);
 
 /*
+ * The same with the weights prepared once per checkpoint instead of converted by every CTA of every call (the module of
+ * early_fusion_vit.py:69-70 keeps its `proj` parameters for the whole run): p3p_patch_embed_prepare writes the 128-channel
+ * tiles of `weight` as tensor-core operand images of `precision` (+ the bias) into blob (p3p_patch_embed_blob_bytes bytes,
+ * device memory, 16-byte aligned); p3p_patch_embed_prepared runs the convolution from it -- bit-identical to
+ * p3p_patch_embed.  weight / bias are still passed (they may be NULL for 8-px patches with a tensor-core precision): shapes
+ * and precisions outside the tensor-core route (other patch sizes, P3P_PRECISION_FP32) read them.
+ */
+size_t p3p_patch_embed_blob_bytes(int32_t channels, int32_t in_chans, int32_t patch);
+int p3p_patch_embed_prepare(const float* weight, const float* bias, int32_t channels, int32_t in_chans, int32_t patch,
+                            int32_t precision, void* blob, size_t blob_bytes, void* stream);
+int p3p_patch_embed_prepared(const float* images, int32_t num_tiles, int32_t in_chans, int32_t height, int32_t width,
+                             int32_t patch, const void* blob, const float* weight, const float* bias, int32_t channels,
+                             int32_t precision, void* out, int32_t out_dtype, int32_t out_layout, int32_t c_total, int32_t c_offset,
+                             void* stream);
+
+/*
  * LiDAR input front end: raw LAS integer coordinates of a jagged batch -> the (total_points, 3)
  * fp32 pixel-space points p3p_encode consumes, bit-identical to the numpy / scikit-learn code of
  * P3Dataset.load_lidar_points (p3_coco.py:74-101; clip = 1) and Predictor.load_lidar_from_file (predictor.py:116-137;

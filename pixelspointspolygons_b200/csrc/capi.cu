@@ -478,7 +478,40 @@ int p3p_patch_embed(const float* images, int32_t num_tiles, int32_t in_chans, in
     if (num_tiles == 0) return P3P_OK;
     if (!images || !weight || !out) return fail(P3P_ERR_INVALID_ARGUMENT, "null images, weight or out");
     if (!aligned16(images) || !aligned16(weight) || !aligned16(out)) return fail(P3P_ERR_INVALID_ARGUMENT, "misaligned pointer");
-    return launch_patch_embed(images, num_tiles, in_chans, height, width, patch, weight, bias, channels, precision, out, out_dtype,
+    return launch_patch_embed(images, num_tiles, in_chans, height, width, patch, weight, bias, nullptr, channels, precision, out,
+                              out_dtype, out_layout, c_total, c_offset, static_cast<cudaStream_t>(stream));
+}
+
+size_t p3p_patch_embed_blob_bytes(int32_t channels, int32_t in_chans, int32_t patch) {
+    if (channels < 1 || in_chans < 1 || patch < 1) return 0;
+    return patch_embed_blob_bytes(channels, in_chans, patch);
+}
+
+int p3p_patch_embed_prepare(const float* weight, const float* bias, int32_t channels, int32_t in_chans, int32_t patch,
+                            int32_t precision, void* blob, size_t blob_bytes, void* stream) {
+    if (channels < 1 || in_chans < 1 || patch < 1) return fail(P3P_ERR_INVALID_ARGUMENT, "channels, in_chans and patch must be positive");
+    if (precision < P3P_PRECISION_FP32 || precision > P3P_PRECISION_FP16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+    if (!weight || !blob) return fail(P3P_ERR_INVALID_ARGUMENT, "null weight or blob");
+    if (!aligned16(weight) || !aligned16(blob)) return fail(P3P_ERR_INVALID_ARGUMENT, "misaligned pointer");
+    if (blob_bytes < patch_embed_blob_bytes(channels, in_chans, patch)) return fail(P3P_ERR_WORKSPACE, "blob of %zu bytes is too small", blob_bytes);
+    return launch_patch_embed_prepare(weight, bias, channels, in_chans, patch, precision, blob, static_cast<cudaStream_t>(stream));
+}
+
+int p3p_patch_embed_prepared(const float* images, int32_t num_tiles, int32_t in_chans, int32_t height, int32_t width,
+                             int32_t patch, const void* blob, const float* weight, const float* bias, int32_t channels,
+                             int32_t precision, void* out, int32_t out_dtype, int32_t out_layout, int32_t c_total, int32_t c_offset,
+                             void* stream) {
+    if (!blob || !aligned16(blob)) return fail(P3P_ERR_INVALID_ARGUMENT, "null or misaligned blob");
+    const int rc = p3p_patch_embed(images, 0, in_chans, height, width, patch, weight, bias, channels, precision, out, out_dtype,
+                                   out_layout, c_total, c_offset, stream);  // (argument checks; no tiles: no launch)
+    if (rc) return rc;
+    if (num_tiles < 0) return fail(P3P_ERR_INVALID_ARGUMENT, "num_tiles %d", num_tiles);
+    if (num_tiles == 0) return P3P_OK;
+    if (!images || !out) return fail(P3P_ERR_INVALID_ARGUMENT, "null images or out");
+    if (!aligned16(images) || !aligned16(out) || (weight && !aligned16(weight))) return fail(P3P_ERR_INVALID_ARGUMENT, "misaligned pointer");
+    // only the tensor-core route reads the blob; shapes it does not cover fall through to the exact kernel and the raw weights
+    return launch_patch_embed(images, num_tiles, in_chans, height, width, patch, weight, bias,
+                              (patch == 8 && precision != P3P_PRECISION_FP32) ? blob : nullptr, channels, precision, out, out_dtype,
                               out_layout, c_total, c_offset, static_cast<cudaStream_t>(stream));
 }
 

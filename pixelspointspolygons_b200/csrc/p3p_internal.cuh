@@ -165,8 +165,10 @@ int launch_pfn_simt(const PfnArgs& a, cudaStream_t st);
 int launch_pfn_tc(const PfnArgs& a, int precision, cudaStream_t st);
 int launch_zero_lidar(const PfnArgs& a, cudaStream_t st);
 int launch_cls_rows(const PfnArgs& a, const float* cls_token, cudaStream_t st);
-int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, int P, const float* weight,
-                       const float* bias, int C, int precision, void* out, int out_dtype, int out_layout, int c_total, int c_offset,
+size_t patch_embed_blob_bytes(int C, int in_chans, int P);
+int launch_patch_embed_prepare(const float* weight, const float* bias, int C, int in_chans, int P, int precision, void* blob, cudaStream_t st);
+int launch_patch_embed(const float* images, int B, int in_chans, int H, int W, int P, const float* weight, const float* bias,
+                       const void* blob, int C, int precision, void* out, int out_dtype, int out_layout, int c_total, int c_offset,
                        cudaStream_t st);
 int launch_las_to_pixels(const int32_t* X, const int32_t* Y, const int32_t* Z, const uint16_t* deltas, const int32_t* base,
                          const int64_t* offsets, int B, int64_t total, const p3p_las_tile* tiles, double z_hi, int32_t* mm, float* out,

@@ -39,6 +39,26 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=bias)
         self.norm = nn.Identity()
         self.precision = precision
+        self._blobs = {}  # (device, precision) -> (parameter stamp, prepared weights)
+
+    def _blob(self, device, precision: str) -> torch.Tensor:
+        """The weights as tensor-core operand tiles (p3p_patch_embed_prepare), re-made when a parameter changes."""
+        tensors = [self.proj.weight, self.proj.bias]
+        stamp = tuple((t._version, t.data_ptr()) if t is not None else None for t in tensors)
+        hit = self._blobs.get((device, precision))
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        w = self.proj.weight.detach().contiguous()
+        b = self.proj.bias.detach().contiguous() if self.proj.bias is not None else None
+        nbytes = _lib.lib().p3p_patch_embed_blob_bytes(self.embed_dim, self.in_chans, self.patch_size)
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().p3p_patch_embed_prepare(w.data_ptr(), b.data_ptr() if b is not None else None, self.embed_dim,
+                                                          self.in_chans, self.patch_size, P3P_PRECISION[precision], blob.data_ptr(),
+                                                          nbytes, torch.cuda.current_stream(device).cuda_stream),
+                       "p3p_patch_embed_prepare")
+        self._blobs[(device, precision)] = (stamp, blob)
+        return blob
 
     def forward_into(self, x: torch.Tensor, out: torch.Tensor, c_total: int, c_offset: int, precision: Optional[str] = None,
                      layout: int = P3P_LAYOUT_NCHW):
@@ -56,12 +76,16 @@ class PatchEmbed(nn.Module):
         need = B * (H // self.patch_size) * (W // self.patch_size) * c_total
         if out.device != x.device or not out.is_contiguous() or out.numel() < need:
             raise ValueError(f"out must be a contiguous tensor of at least {need} elements on {x.device}")
+        precision = precision or self.precision
+        if w.device != x.device or w.dtype != torch.float32:
+            raise RuntimeError("PatchEmbed parameters must be float32 on the device of x_image")
         with torch.cuda.device(x.device):
-            rc = _lib.lib().p3p_patch_embed(x.data_ptr(), B, self.in_chans, H, W, self.patch_size, w.data_ptr(),
-                                            b.data_ptr() if b is not None else None, self.embed_dim,
-                                            P3P_PRECISION[precision or self.precision], out.data_ptr(), dt, layout, c_total, c_offset,
-                                            torch.cuda.current_stream(x.device).cuda_stream)
-        _lib.check(rc, "p3p_patch_embed")
+            blob = self._blob(x.device, precision)
+            rc = _lib.lib().p3p_patch_embed_prepared(x.data_ptr(), B, self.in_chans, H, W, self.patch_size, blob.data_ptr(),
+                                                     w.data_ptr(), b.data_ptr() if b is not None else None, self.embed_dim,
+                                                     P3P_PRECISION[precision], out.data_ptr(), dt, layout, c_total, c_offset,
+                                                     torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(rc, "p3p_patch_embed_prepared")
         return out
 
     def forward(self, x):

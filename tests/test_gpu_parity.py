@@ -483,6 +483,38 @@ def test_patch_embed_matches_conv2d(cuda_device, prec):
     assert_close(buf[:, :384], r, max(TOL[prec], 8e-3), f"patch embed {prec} bf16 out")
 
 
+@pytest.mark.parametrize("prec", ["tf32", "fp16", "bf16"])
+def test_patch_embed_prepared_weights_equal_raw_weights(cuda_device, prec):
+    """p3p_patch_embed_prepared (weights stored once as operand tiles, copied by TMA) against p3p_patch_embed (every CTA
+    converts the raw weights): the same bits, both layouts, a channel count that is not a multiple of 128, and a parameter
+    update that must invalidate the cached tiles."""
+    import ctypes as C
+
+    from pixelspointspolygons_b200 import _lib
+    from pixelspointspolygons_b200.fusion import PatchEmbed
+
+    g = torch.Generator().manual_seed(21)
+    for dim in (384, 200):
+        pe = PatchEmbed(224, 8, 3, dim, precision=prec).to(cuda_device).eval()
+        with torch.no_grad():
+            pe.proj.weight.copy_(torch.randn(pe.proj.weight.shape, generator=g) * 0.1)
+            pe.proj.bias.copy_(torch.randn(dim, generator=g) * 0.1)
+        img = ((torch.rand(5, 3, 224, 224, generator=g) - 0.5) * 3.0).to(cuda_device)
+        for layout, shape in ((0, (5, dim, 28, 28)), (1, (5, 784, dim))):
+            raw = torch.zeros(shape, device=cuda_device)
+            w, b = pe.proj.weight.detach().contiguous(), pe.proj.bias.detach().clone()
+            rc = _lib.lib().p3p_patch_embed(img.data_ptr(), 5, 3, 224, 224, 8, w.data_ptr(), b.data_ptr(), dim, _lib.P3P_PRECISION[prec],
+                                            raw.data_ptr(), 0, layout, dim, 0, torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "p3p_patch_embed")
+            got = pe.forward_into(img, torch.zeros(shape, device=cuda_device), dim, 0, layout=layout)
+            assert torch.equal(got, raw), (prec, dim, layout)
+        with torch.no_grad():
+            pe.proj.weight.mul_(2.0)  # in-place update: new version counter, the tiles are re-made
+            pe.proj.bias.zero_()
+        again = pe.forward_into(img, torch.zeros(shape, device=cuda_device), dim, 0, layout=1)
+        assert torch.allclose(again, got * 2.0 - 2.0 * b.view(1, 1, -1), rtol=1e-5, atol=1e-5)
+
+
 def test_patch_embed_other_shapes_take_the_exact_route(cuda_device):
     from pixelspointspolygons_b200.fusion import PatchEmbed
 
