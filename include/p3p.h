@@ -285,6 +285,58 @@ int p3p_upsample_bilinear_nhwc16(const float* x, int32_t num_tiles, int32_t h, i
                                  int64_t src_batch_stride, int32_t out_h, int32_t out_w, int32_t precision, void* out, void* stream);
 
 /*
+ * PFN + scatter over the pillar table a p3p_voxelize call (same num_tiles / total_points, same stream) left in
+ * `workspace`: the second half of p3p_encode, for callers that need the voxelizer's result for more than one pass
+ * (the training step below).  Arguments as in p3p_encode.
+ */
+int p3p_encode_workspace(const p3p_grid* grid, int32_t num_tiles, int64_t total_points, const void* blob, int32_t channels,
+                         int32_t precision, void* out, int32_t out_layout, int32_t out_dtype, int32_t c_total, int32_t c_offset,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * SURVEY 8f rank 4 -- the training step of the PillarFeatureNet (`module.train()`): what autograd does through Open3D-ML's
+ * PillarFeatureNet / PFNLayer x2 (call site pointpillars_o3d.py:93; DDP + SyncBatchNorm wrap
+ * R:pixelspointspolygons/models/pix2poly/model_pix2poly.py:326-328), without any (V, M, *) tensor.  `params` carries the
+ * RAW parameters (the norm*_mean / norm*_var pointers are ignored: the batch statistics live in `state`); `workspace` must
+ * hold the pillar table of a p3p_voxelize call on the same batch and stay untouched until the backward has run.
+ *
+ * state: p3p_pfn_train_state_doubles(C, offsets) doubles on the device.  offsets[13] (in doubles) =
+ *   { mom0, sums0, bn0, mom1, sums1, bn1, back1, back1g, A1, kq, back0, back0g, A0 }.  The regions a multi-rank caller
+ *   touches between the calls (SyncBatchNorm: one all-reduce(sum) each):
+ *     sums0  [65]      sum y0 (32), sum y0^2 (32), rows        after p3p_pfn_train_stats0
+ *     sums1  [2C + 1]  sum y1 (C),  sum y1^2 (C),  rows        after p3p_pfn_train_stats1
+ *     back1g [2C]      dbeta1, dgamma1: copy of back1 (this rank's sums), then all-reduced, before p3p_pfn_backward2
+ *     back0g [64]      the same for layer 0 (copy of back0), before p3p_pfn_backward3
+ *   A single-rank caller only does the two copies.
+ *
+ * forward:  p3p_pfn_train_stats0 -> [all-reduce sums0] -> p3p_pfn_train_stats1 -> [all-reduce sums1] ->
+ *           p3p_pfn_train_forward (out: (B, ny nx, C) fp32 token rows, exact fp32; route: p3p_pfn_train_route_bytes bytes
+ *           that carry the winning rows to the backward) and p3p_pfn_train_stats2 (batch mean / biased variance of both
+ *           layers as fp32, for the running-statistics update; folded with p3p_pfn_prepare they also drive the inference
+ *           kernels through p3p_encode_workspace when a tensor-core forward is preferred).
+ * backward: p3p_pfn_backward1 (grad_out, out: (B, ny nx, C) fp32 rows, route as left by the forward) ->
+ *           [back1g] -> p3p_pfn_backward2 -> [back0g] -> p3p_pfn_backward3 (gradients of the six parameters, fp32,
+ *           this rank's share: DDP averages them as it does for the reference).
+ * Covers C <= 512 and max_points <= 512.
+ */
+int64_t p3p_pfn_train_state_doubles(int32_t channels, int64_t* offsets);
+size_t p3p_pfn_train_route_bytes(const p3p_grid* grid, int32_t num_tiles, int32_t channels);
+int p3p_pfn_train_stats0(const p3p_grid* grid, int32_t num_tiles, int64_t total_points, const p3p_pfn_params* params,
+                         double* state, void* workspace, size_t workspace_bytes, void* stream);
+int p3p_pfn_train_stats1(const p3p_grid* grid, int32_t num_tiles, int64_t total_points, const p3p_pfn_params* params,
+                         double* state, void* workspace, size_t workspace_bytes, void* stream);
+int p3p_pfn_train_stats2(const p3p_pfn_params* params, double* state, float* mean0, float* var0, float* mean1, float* var1,
+                         void* stream);
+int p3p_pfn_train_forward(const p3p_grid* grid, int32_t num_tiles, int64_t total_points, const p3p_pfn_params* params,
+                          double* state, float* out, void* route, void* workspace, size_t workspace_bytes, void* stream);
+int p3p_pfn_backward1(const p3p_grid* grid, int32_t num_tiles, int64_t total_points, const p3p_pfn_params* params, double* state,
+                      const float* grad_out, const float* out, void* route, void* workspace, size_t workspace_bytes, void* stream);
+int p3p_pfn_backward2(const p3p_grid* grid, int32_t num_tiles, int64_t total_points, const p3p_pfn_params* params, double* state,
+                      const void* route, void* workspace, size_t workspace_bytes, void* stream);
+int p3p_pfn_backward3(const p3p_pfn_params* params, const double* state, float* d_linear0, float* d_norm0_weight,
+                      float* d_norm0_bias, float* d_linear1, float* d_norm1_weight, float* d_norm1_bias, void* stream);
+
+/*
  * Measurement hooks (bench.py's roofline leg; no reference counterpart).  Between begin and end every
  * p3p_encode call made by this thread records CUDA events around its two kernels on the caller's stream.
  * p3p_profile_end synchronises those events and returns, per recorded call, the milliseconds of the

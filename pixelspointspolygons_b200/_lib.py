@@ -18,6 +18,8 @@ EXPORTED = [
     "p3p_profile_begin", "p3p_profile_end", "p3p_conv3x3_blob_bytes", "p3p_conv3x3_prepare", "p3p_conv3x3",
     "p3p_nchw_to_nhwc16", "p3p_upsample_bilinear_nhwc16", "p3p_las_packed_to_pixels",
     "p3p_patch_embed_blob_bytes", "p3p_patch_embed_prepare", "p3p_patch_embed_prepared",
+    "p3p_encode_workspace", "p3p_pfn_train_state_doubles", "p3p_pfn_train_route_bytes", "p3p_pfn_train_stats0",
+    "p3p_pfn_train_stats1", "p3p_pfn_train_stats2", "p3p_pfn_train_forward", "p3p_pfn_backward1", "p3p_pfn_backward2", "p3p_pfn_backward3",
 ]
 
 
@@ -113,6 +115,25 @@ def lib():
     l.p3p_nchw_to_nhwc16.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp]
     l.p3p_upsample_bilinear_nhwc16.restype = C.c_int
     l.p3p_upsample_bilinear_nhwc16.argtypes = [vp, i32, i32, i32, i32, i64, i32, i32, i32, vp, vp]
+    l.p3p_encode_workspace.restype = C.c_int
+    l.p3p_encode_workspace.argtypes = [C.POINTER(Grid), i32, i64, vp, i32, i32, vp, i32, i32, i32, i32, vp, sz, vp]
+    l.p3p_pfn_train_state_doubles.restype = i64
+    l.p3p_pfn_train_state_doubles.argtypes = [i32, C.POINTER(i64)]
+    l.p3p_pfn_train_route_bytes.restype = sz
+    l.p3p_pfn_train_route_bytes.argtypes = [C.POINTER(Grid), i32, i32]
+    for name in ("p3p_pfn_train_stats0", "p3p_pfn_train_stats1"):
+        getattr(l, name).restype = C.c_int
+        getattr(l, name).argtypes = [C.POINTER(Grid), i32, i64, C.POINTER(PfnParams), vp, vp, sz, vp]
+    l.p3p_pfn_train_stats2.restype = C.c_int
+    l.p3p_pfn_train_stats2.argtypes = [C.POINTER(PfnParams), vp, vp, vp, vp, vp, vp]
+    l.p3p_pfn_backward1.restype = C.c_int
+    l.p3p_pfn_backward1.argtypes = [C.POINTER(Grid), i32, i64, C.POINTER(PfnParams), vp, vp, vp, vp, vp, sz, vp]
+    l.p3p_pfn_train_forward.restype = C.c_int
+    l.p3p_pfn_train_forward.argtypes = [C.POINTER(Grid), i32, i64, C.POINTER(PfnParams), vp, vp, vp, vp, sz, vp]
+    l.p3p_pfn_backward2.restype = C.c_int
+    l.p3p_pfn_backward2.argtypes = [C.POINTER(Grid), i32, i64, C.POINTER(PfnParams), vp, vp, vp, sz, vp]
+    l.p3p_pfn_backward3.restype = C.c_int
+    l.p3p_pfn_backward3.argtypes = [C.POINTER(PfnParams), vp, vp, vp, vp, vp, vp, vp, vp]
     l.p3p_profile_begin.restype = C.c_int
     l.p3p_profile_begin.argtypes = [i32]
     l.p3p_profile_end.restype = C.c_int

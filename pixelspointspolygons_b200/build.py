@@ -11,7 +11,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 # P3P_LIB selects another build of the same library (kernel experiments: tools/build_variant.py); the product default is in-tree
 LIB_PATH = os.environ.get("P3P_LIB") or os.path.join(_HERE, "libp3p.so")
-SOURCES = ["capi.cu", "voxelize.cu", "pfn.cu", "patch_embed.cu", "las.cu", "conv3x3.cu"]
+SOURCES = ["capi.cu", "voxelize.cu", "pfn.cu", "patch_embed.cu", "las.cu", "conv3x3.cu", "pfn_train.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--cudart", "static",

@@ -137,6 +137,8 @@ int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out)
     l.off_tile_hi = take((size_t)B * sizeof(int32_t));
     l.off_owner = take((size_t)B * HW * sizeof(int32_t));
     l.off_cell_desc = take((size_t)B * HW * sizeof(int32_t));
+    l.off_train_list = take((size_t)B * g.Vmax * sizeof(int4));
+    l.off_train_count = take(4 * sizeof(int32_t));
     l.total_bytes = off;
     *out = l;
     return P3P_OK;
@@ -322,6 +324,43 @@ int p3p_encode(const float* points, int32_t point_stride, const int64_t* tile_of
         ++g_prof.used;
     }
     return rc;
+}
+
+int p3p_encode_workspace(const p3p_grid* grid, int32_t num_tiles, int64_t total_points, const void* blob, int32_t channels,
+                         int32_t precision, void* out, int32_t out_layout, int32_t out_dtype, int32_t c_total, int32_t c_offset,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    GridDev g;
+    WsLayout l;
+    BlobLayout bl;
+    int rc = make_grid(grid, &g);
+    if (rc) return rc;
+    rc = make_ws_layout(g, num_tiles, total_points, &l);
+    if (rc) return rc;
+    rc = check_blob(channels, &bl);
+    if (rc) return rc;
+    if (!blob || !out || !workspace) return fail(P3P_ERR_INVALID_ARGUMENT, "null blob, out or workspace");
+    if (!aligned16(blob) || !aligned16(out) || !aligned16(workspace)) return fail(P3P_ERR_INVALID_ARGUMENT, "misaligned pointer");
+    if (workspace_bytes < l.total_bytes) return fail(P3P_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", l.total_bytes, workspace_bytes);
+    if (out_layout != P3P_LAYOUT_NCHW && out_layout != P3P_LAYOUT_NLC) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown layout %d", out_layout);
+    if (out_dtype != P3P_DTYPE_F32 && out_dtype != P3P_DTYPE_BF16 && out_dtype != P3P_DTYPE_F16) return fail(P3P_ERR_INVALID_ARGUMENT, "unknown dtype %d", out_dtype);
+    if ((out_layout == P3P_LAYOUT_NCHW || c_total > 0) && (c_offset < 0 || c_offset + channels > c_total))
+        return fail(P3P_ERR_INVALID_ARGUMENT, "channels [%d, %d) outside c_total %d", c_offset, c_offset + channels, c_total);
+    if (num_tiles == 0) return P3P_OK;
+    PfnArgs a;
+    fill_pfn_args(&a, g, ws_ptrs(workspace, l), blob, bl, num_tiles);
+    a.item_mode = kItemsCanvas;
+    a.items_per_tile = g.ny * g.nx;
+    a.num_items = (int64_t)num_tiles * a.items_per_tile;
+    a.out = out;
+    a.out_layout = out_layout;
+    a.out_dtype = out_dtype;
+    a.c_total = c_total;
+    a.c_offset = c_offset;
+    if (out_layout == P3P_LAYOUT_NLC && c_total > 0) {
+        a.row_stride = c_total;
+        a.row_offset = c_offset;
+    }
+    return run_pfn(a, precision, static_cast<cudaStream_t>(stream));
 }
 
 int p3p_encode_tokens(const float* points, int32_t point_stride, const int64_t* tile_offsets, int32_t num_tiles,

@@ -67,6 +67,8 @@ struct WsLayout {
     size_t off_tile_hi;    // int32  [B]             bit 0: keys beyond the regular cells in use; bit 1: owner table written without a plan
     size_t off_owner;      // int32  [B][ny*nx]      voxel ordinal owning the canvas cell, -1 = empty
     size_t off_cell_desc;  // int32  [B][ny*nx]      key | n << 16 of the owning pillar, -1 = empty
+    size_t off_train_list; // int4   [B][Vmax]       training kernels: the batch's pillars, compacted (pfn_train.cu)
+    size_t off_train_count;// int32  [4]             their number
     size_t total_bytes;
 };
 
@@ -89,6 +91,8 @@ struct WsPtrs {
     int32_t* tile_hi;
     int32_t* owner;
     int32_t* cell_desc;
+    int4* train_list;
+    int32_t* train_count;
 };
 
 inline WsPtrs ws_ptrs(void* base, const WsLayout& l) {
@@ -108,6 +112,8 @@ inline WsPtrs ws_ptrs(void* base, const WsLayout& l) {
     p.tile_hi = reinterpret_cast<int32_t*>(b + l.off_tile_hi);
     p.owner = reinterpret_cast<int32_t*>(b + l.off_owner);
     p.cell_desc = reinterpret_cast<int32_t*>(b + l.off_cell_desc);
+    p.train_list = reinterpret_cast<int4*>(b + l.off_train_list);
+    p.train_count = reinterpret_cast<int32_t*>(b + l.off_train_count);
     return p;
 }
 

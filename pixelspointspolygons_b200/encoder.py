@@ -293,7 +293,7 @@ class PointPillarsEncoder(nn.Module):
 
     def forward(self, x_lidar, return_flattened: bool = True):
         if self.training:
-            return self._forward_dense(x_lidar, return_flattened)
+            return self._forward_train(x_lidar, return_flattened)
         if isinstance(x_lidar, (list, tuple)):  # pack once (encode_into accepts the jagged pair as is)
             values, offsets, B = self._pack(x_lidar)
             x_lidar = torch.nested.nested_tensor_from_jagged(values, offsets)
@@ -356,12 +356,30 @@ class PointPillarsEncoder(nn.Module):
         mask = torch.arange(V, device=device).view(1, -1) < r["num_pillars"].view(-1, 1)
         return feats[mask], r["pillar_coords"][mask]
 
-    def _forward_dense(self, x_lidar, return_flattened: bool):
-        """Training step: CUDA voxelizer (no grad, like the reference's @torch.no_grad voxelize) + dense autograd PFN
-        with BatchNorm batch statistics / SyncBatchNorm, then the scatter.  Not the measured path."""
+    def _forward_train(self, x_lidar, return_flattened: bool):
+        """Training step on the fused kernels: CUDA voxelizer (no grad, like the reference's @torch.no_grad
+        voxelize), BatchNorm batch statistics of both PFN layers (SyncBatchNorm: exchanged over the layer's process group),
+        the PFN + scatter in exact fp32 (dividing by the batch's own standard deviation amplifies the operand rounding of the
+        tensor-core modes: 2e-3 of scale measured with tf32), and a fused backward to the six PFN parameters -- one autograd
+        node (train.FusedPFNTrain)."""
+        from .train import FusedPFNTrain
+        values, offsets, B = self._pack(x_lidar)
+        l0, l1 = self.voxel_encoder.pfn_layers[0], self.voxel_encoder.pfn_layers[1]
+        x = FusedPFNTrain.apply(self, values, offsets, B, l0.linear.weight, l0.norm.weight,
+                                l0.norm.bias, l1.linear.weight, l1.norm.weight, l1.norm.bias)
+        if return_flattened:
+            return x
+        return x.transpose(1, 2).reshape(B, self.channels, self.ny, self.nx)
+
+    def forward_dense_reference(self, x_lidar, return_flattened: bool = True, voxel_encoder: Optional[nn.Module] = None):
+        """The same training step written as the reference has it: CUDA voxelizer + the dense autograd PillarFeatureNet of
+        this file (BatchNorm1d batch statistics over every slot) + index-put scatter.  Kept as the checker of the fused
+        training path in tests/ (gradients, running statistics; `voxel_encoder`: e.g. a float64 copy of the module's);
+        nothing in the package calls it."""
         voxels, num_points, coors = self.voxelize(x_lidar)
         B = len(x_lidar) if isinstance(x_lidar, (list, tuple)) else x_lidar.shape[0]
-        feats = self.voxel_encoder(voxels, num_points, coors, self.center_alias)
+        ve = voxel_encoder if voxel_encoder is not None else self.voxel_encoder
+        feats = ve(voxels.to(ve.pfn_layers[0].linear.weight.dtype), num_points, coors, self.center_alias)
         hw = self.ny * self.nx
         canvas = feats.new_zeros(B * hw, self.channels)
         flat = coors[:, 0].long() * hw + coors[:, 2].long() * self.nx + coors[:, 3].long()
