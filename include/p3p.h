@@ -300,8 +300,8 @@ int p3p_encode_workspace(const p3p_grid* grid, int32_t num_tiles, int64_t total_
  * RAW parameters (the norm*_mean / norm*_var pointers are ignored: the batch statistics live in `state`); `workspace` must
  * hold the pillar table of a p3p_voxelize call on the same batch and stay untouched until the backward has run.
  *
- * state: p3p_pfn_train_state_doubles(C, offsets) doubles on the device.  offsets[13] (in doubles) =
- *   { mom0, sums0, bn0, mom1, sums1, bn1, back1, back1g, A1, kq, back0, back0g, A0 }.  The regions a multi-rank caller
+ * state: p3p_pfn_train_state_doubles(C, offsets) doubles on the device.  offsets[14] (in doubles) =
+ *   { mom0, sums0, bn0, mom1, sums1, bn1, cen, back1, back1g, A1, kq, back0, back0g, A0 }.  The regions a multi-rank caller
  *   touches between the calls (SyncBatchNorm: one all-reduce(sum) each):
  *     sums0  [65]      sum y0 (32), sum y0^2 (32), rows        after p3p_pfn_train_stats0
  *     sums1  [2C + 1]  sum y1 (C),  sum y1^2 (C),  rows        after p3p_pfn_train_stats1

@@ -41,7 +41,7 @@ constexpr int kXS = 36;  // floats per x0 / yh0 row in shared memory (16-byte al
 
 struct TrainLayout {
     int C;
-    int64_t mom0, sums0, bn0, mom1, sums1, bn1, back1, back1g, A1, kq, back0, back0g, A0, total;
+    int64_t mom0, sums0, bn0, mom1, sums1, bn1, cen, back1, back1g, A1, kq, back0, back0g, A0, total;
 };
 TrainLayout make_train_layout(int C) {
     TrainLayout l;
@@ -54,6 +54,7 @@ TrainLayout make_train_layout(int C) {
     l.mom1 = take(64 + 4096);         // sum z [64], Z[64][64]
     l.sums1 = take(2 * (int64_t)C + 1);
     l.bn1 = take(2 * (int64_t)C);
+    l.cen = take(65);                 // centre of the layer-1 moment accumulation: sum z over a sample of pillars [64], its rows
     l.back1 = take(2 * (int64_t)C);   // dbeta1 [C], dgamma1 [C] of this rank
     l.back1g = take(2 * (int64_t)C);  // the same summed over the ranks of the SyncBatchNorm group
     l.A1 = take((int64_t)C * 64);
@@ -301,8 +302,9 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward statistics (moments in float64: the products of fp32 inputs are exact, so the centred second moments the
-// variance and the backward need do not lose digits to E[y^2] - E[y]^2)
+// forward statistics.  This GPU's fp64 pipe issues about one lane per clock and SM, so the moments are accumulated in
+// fp32 about a centre close to the mean (then nothing cancels in E[y^2] - E[y]^2 and in the centred second moments of the
+// backward) and only merged in float64.  Layer 0: the decorated channels are offsets, centre 0 is close enough.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) train_stats0_kernel(TrainArgs a) {
     extern __shared__ __align__(16) float smem_f[];
@@ -310,11 +312,11 @@ __global__ void __launch_bounds__(256) train_stats0_kernel(TrainArgs a) {
     __shared__ double acc[45];
     const int tid = threadIdx.x;
     if (tid < 45) acc[tid] = 0.0;
-    double m1[8], m2[36];
+    float m1[8], m2[36];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m1[i] = 0.0;
+    for (int i = 0; i < 8; ++i) m1[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 36; ++i) m2[i] = 0.0;
+    for (int i = 0; i < 36; ++i) m2[i] = 0.f;
     int pillars = 0;
     Walk w;
     walk_begin(w, a);
@@ -324,15 +326,15 @@ __global__ void __launch_bounds__(256) train_stats0_kernel(TrainArgs a) {
         ++pillars;
         decorate(a, p, slots_of(a, w.d0), w.q0, s);
         for (int r = tid; r < p.n; r += blockDim.x) {
-            double d[8];
+            float d[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) d[i] = (double)s.D[(size_t)r * 8 + i];
+            for (int i = 0; i < 8; ++i) d[i] = s.D[(size_t)r * 8 + i];
             int e = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 m1[i] += d[i];
 #pragma unroll
-                for (int j = i; j < 8; ++j) { m2[e] = fma(d[i], d[j], m2[e]); ++e; }
+                for (int j = i; j < 8; ++j) { m2[e] = __fmaf_rn(d[i], d[j], m2[e]); ++e; }
             }
         }
         __syncthreads();
@@ -340,12 +342,12 @@ __global__ void __launch_bounds__(256) train_stats0_kernel(TrainArgs a) {
     const int lane = tid & 31;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const double v = warp_sum_d(m1[i]);
+        const double v = warp_sum_d((double)m1[i]);
         if (lane == 0) atomicAdd(&acc[1 + i], v);
     }
 #pragma unroll
     for (int e = 0; e < 36; ++e) {
-        const double v = warp_sum_d(m2[e]);
+        const double v = warp_sum_d((double)m2[e]);
         if (lane == 0) atomicAdd(&acc[9 + e], v);
     }
     if (tid == 0) acc[0] = (double)pillars * (double)a.g.M;
@@ -405,15 +407,48 @@ __global__ void train_bn_kernel(const double* __restrict__ sums, int C, double* 
     if (var_f) var_f[c] = (float)var;
 }
 
+// centre of the layer-1 moments: sum of z over a sample of the batch's pillars (any point within a spread of the mean
+// will do; hmax in particular has a mean many times its spread)
+constexpr int kCentreCtas = 32, kCentrePillars = 4;
+__global__ void __launch_bounds__(256) train_centre_kernel(TrainArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    const Smem s = carve(smem_f, a.g.M, false);
+    const int tid = threadIdx.x;
+    load_layer0(a, s);
+    __syncthreads();
+    const int count = a.ws.train_count[0];
+    double* cen = a.st + a.tl.cen;
+    for (int t = 0, i = blockIdx.x; t < kCentrePillars && i < count; ++t, i += gridDim.x) {
+        const int4 d = a.ws.train_list[i];
+        const Pillar p = unpack(a, d);
+        const float4* slot = slots_of(a, d);
+        const float4 q0 = tid < p.n ? slot[tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+        decorate(a, p, slot, q0, s);
+        layer0_rows<false>(a, p, s);
+        if (tid < 32) {
+            atomicAdd(cen + tid, (double)s.sx[tid]);
+            atomicAdd(cen + 32 + tid, (double)((float)a.g.M * s.hmax[tid]));
+        }
+        if (tid == 0) atomicAdd(cen + 64, (double)a.g.M);
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) train_stats1_kernel(TrainArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const Smem s = carve(smem_f, a.g.M, false);
+    float* cz = s.extra;  // [64] centre
     const int tid = threadIdx.x, M = a.g.M;
     load_layer0(a, s);
+    if (tid < 64) {
+        const double* cen = a.st + a.tl.cen;
+        cz[tid] = cen[64] > 0.0 ? (float)(cen[tid] / cen[64]) : 0.f;
+    }
     __syncthreads();
     const int i0 = (tid >> 4) * 2, j0 = (tid & 15) * 2;
-    double aX[4] = {0, 0, 0, 0}, aC[4] = {0, 0, 0, 0}, aH[4] = {0, 0, 0, 0}, aS = 0.0, aSh = 0.0;
-    double* XD = reinterpret_cast<double*>(s.extra);  // [64][32] one chunk of rows in float64 (16-byte aligned)
+    const float ci0 = cz[i0], ci1 = cz[i0 + 1], cj0 = cz[j0], cj1 = cz[j0 + 1];
+    const float chi0 = cz[32 + i0], chi1 = cz[32 + i0 + 1], chj0 = cz[32 + j0], chj1 = cz[32 + j0 + 1];
+    float aX[4] = {0, 0, 0, 0}, aC[4] = {0, 0, 0, 0}, aH[4] = {0, 0, 0, 0}, aS = 0.f, aSh = 0.f;
     Walk w;
     walk_begin(w, a);
     for (; w.i < w.count; walk_next(w)) {
@@ -421,26 +456,24 @@ __global__ void __launch_bounds__(256) train_stats1_kernel(TrainArgs a) {
         const Pillar p = unpack(a, w.d0);
         decorate(a, p, slots_of(a, w.d0), w.q0, s);
         const int rows = layer0_rows<false>(a, p, s);
-        // second moments of x0 in float64 (exact products); the rows are converted once per chunk of 64, not once per use
-        for (int base = 0; base < rows; base += 64) {
-            const int nr = min(64, rows - base);
-            for (int e = tid; e < nr * 32; e += blockDim.x)
-                XD[e] = (double)s.X0[(size_t)(base + (e >> 5)) * kXS + (e & 31)] * ((base + (e >> 5) < p.n) ? 1.0 : sqrt((double)(M - p.n)));
-            __syncthreads();
-            for (int r = 0; r < nr; ++r) {
-                const double2 xi = *reinterpret_cast<const double2*>(XD + r * 32 + i0);
-                const double2 xj = *reinterpret_cast<const double2*>(XD + r * 32 + j0);
-                aX[0] = fma(xi.x, xj.x, aX[0]); aX[1] = fma(xi.x, xj.y, aX[1]);
-                aX[2] = fma(xi.y, xj.x, aX[2]); aX[3] = fma(xi.y, xj.y, aX[3]);
-            }
-            __syncthreads();
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < rows; ++r) {
+            const float wt = (r < p.n) ? 1.f : (float)(M - p.n);
+            const float2 vi = *reinterpret_cast<const float2*>(s.X0 + (size_t)r * kXS + i0);
+            const float2 vj = *reinterpret_cast<const float2*>(s.X0 + (size_t)r * kXS + j0);
+            const float xi0 = (vi.x - ci0) * wt, xi1 = (vi.y - ci1) * wt, xj0 = vj.x - cj0, xj1 = vj.y - cj1;
+            x[0] = __fmaf_rn(xi0, xj0, x[0]); x[1] = __fmaf_rn(xi0, xj1, x[1]);
+            x[2] = __fmaf_rn(xi1, xj0, x[2]); x[3] = __fmaf_rn(xi1, xj1, x[3]);
         }
-        const double hi0 = s.hmax[i0], hi1 = s.hmax[i0 + 1], hj0 = s.hmax[j0], hj1 = s.hmax[j0 + 1];
-        const double si0 = s.sx[i0], si1 = s.sx[i0 + 1], fm = (double)M;
-        aC[0] = fma(si0, hj0, aC[0]); aC[1] = fma(si0, hj1, aC[1]); aC[2] = fma(si1, hj0, aC[2]); aC[3] = fma(si1, hj1, aC[3]);
-        aH[0] = fma(fm * hi0, hj0, aH[0]); aH[1] = fma(fm * hi0, hj1, aH[1]);
-        aH[2] = fma(fm * hi1, hj0, aH[2]); aH[3] = fma(fm * hi1, hj1, aH[3]);
-        if (tid < 32) { aS += (double)s.sx[tid]; aSh += fm * (double)s.hmax[tid]; }
+        const float fm = (float)M;
+        const float hi0 = s.hmax[i0] - chi0, hi1 = s.hmax[i0 + 1] - chi1, hj0 = s.hmax[j0] - chj0, hj1 = s.hmax[j0 + 1] - chj1;
+        const float si0 = s.sx[i0] - fm * ci0, si1 = s.sx[i0 + 1] - fm * ci1;
+        aX[0] += x[0]; aX[1] += x[1]; aX[2] += x[2]; aX[3] += x[3];
+        aC[0] = __fmaf_rn(si0, hj0, aC[0]); aC[1] = __fmaf_rn(si0, hj1, aC[1]);
+        aC[2] = __fmaf_rn(si1, hj0, aC[2]); aC[3] = __fmaf_rn(si1, hj1, aC[3]);
+        aH[0] = __fmaf_rn(fm * hi0, hj0, aH[0]); aH[1] = __fmaf_rn(fm * hi0, hj1, aH[1]);
+        aH[2] = __fmaf_rn(fm * hi1, hj0, aH[2]); aH[3] = __fmaf_rn(fm * hi1, hj1, aH[3]);
+        if (tid < 32) { aS += s.sx[tid] - fm * cz[tid]; aSh += fm * (s.hmax[tid] - cz[32 + tid]); }
         __syncthreads();
     }
     double* sz = a.st + a.tl.mom1;
@@ -448,12 +481,32 @@ __global__ void __launch_bounds__(256) train_stats1_kernel(TrainArgs a) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int i = i0 + (e >> 1), j = j0 + (e & 1);
-        atomicAdd(Z + i * 64 + j, aX[e]);
-        atomicAdd(Z + i * 64 + 32 + j, aC[e]);
-        atomicAdd(Z + (32 + j) * 64 + i, aC[e]);
-        atomicAdd(Z + (32 + i) * 64 + 32 + j, aH[e]);
+        atomicAdd(Z + i * 64 + j, (double)aX[e]);
+        atomicAdd(Z + i * 64 + 32 + j, (double)aC[e]);
+        atomicAdd(Z + (32 + j) * 64 + i, (double)aC[e]);
+        atomicAdd(Z + (32 + i) * 64 + 32 + j, (double)aH[e]);
     }
-    if (tid < 32) { atomicAdd(sz + tid, aS); atomicAdd(sz + 32 + tid, aSh); }
+    if (tid < 32) { atomicAdd(sz + tid, (double)aS); atomicAdd(sz + 32 + tid, (double)aSh); }
+}
+
+// centred -> raw moments, in float64: Z += c szc^T + szc c^T + R c c^T, sz = szc + R c
+__global__ void __launch_bounds__(1024) train_uncentre_kernel(TrainArgs a) {
+    __shared__ double c[64], szc[64];
+    const int tid = threadIdx.x;
+    const double R = a.st[a.tl.mom0];
+    double* sz = a.st + a.tl.mom1;
+    double* Z = sz + 64;
+    const double* cen = a.st + a.tl.cen;
+    if (tid < 64) {
+        c[tid] = cen[64] > 0.0 ? (double)(float)(cen[tid] / cen[64]) : 0.0;  // (the fp32 value the kernel subtracted)
+        szc[tid] = sz[tid];
+    }
+    __syncthreads();
+    for (int e = tid; e < 4096; e += blockDim.x) {
+        const int i = e >> 6, j = e & 63;
+        Z[e] += c[i] * szc[j] + szc[i] * c[j] + R * c[i] * c[j];
+    }
+    if (tid < 64) sz[tid] = szc[tid] + R * c[tid];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -527,7 +580,7 @@ __global__ void __launch_bounds__(512) train_back1_kernel(TrainArgs a) {
     float wr[64];  // raw row of W1
 #pragma unroll
     for (int j = 0; j < 64; ++j) wr[j] = a.W1[(size_t)c * 64 + j];
-    double dbeta = 0.0, dgamma = 0.0;
+    float dbeta = 0.f, dgamma = 0.f;  // (fp32 over this CTA's pillars, float64 across CTAs)
     __syncthreads();
     Walk w;
     walk_begin(w, a);
@@ -571,16 +624,16 @@ __global__ void __launch_bounds__(512) train_back1_kernel(TrainArgs a) {
                     y = __fmaf_rn(wr[32 + k], h, y);
                     A1s[(32 + k) * C + tid] = __fmaf_rn(du, h, A1s[(32 + k) * C + tid]);
                 }
-                dbeta += (double)du;
-                dgamma += (double)(du * ((y - mu1) * rs1));
+                dbeta += du;
+                dgamma = __fmaf_rn(du, (y - mu1) * rs1, dgamma);
             }
         }
         __syncthreads();
     }
     if (tid < C) {
         double* back = a.st + a.tl.back1;
-        atomicAdd(back + tid, dbeta);
-        atomicAdd(back + C + tid, dgamma);
+        atomicAdd(back + tid, (double)dbeta);
+        atomicAdd(back + C + tid, (double)dgamma);
         double* A1 = a.st + a.tl.A1;
         for (int j = 0; j < 64; ++j) {
             const float v = A1s[j * C + tid];
@@ -640,7 +693,9 @@ __global__ void __launch_bounds__(256) train_back2_kernel(TrainArgs a) {
     int* ams = reinterpret_cast<int*>(dus + C);       // [C]  its arg max rows
     float* coef = reinterpret_cast<float*>(ams + C);  // [C]  a1_c
     float* G = coef + C;                              // [M + 1][33]  x0 half of the dz rows
-    double* accd = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(G + (size_t)(M + 1) * 33) + 7) & ~(uintptr_t)7);  // [32] dbeta0, [32] dgamma0, [256] A0
+    float* accf = G + (size_t)(M + 1) * 33;           // [8][32][10] per-thread partials at the end
+    int* hist = reinterpret_cast<int*>(accf + 8 * 32 * 10);  // [M + 2] channels per winning row, then their prefix
+    int* order = hist + M + 2;                         // [C] channels sorted by winning row
     load_layer0(a, s);
     const double* bn1 = a.st + a.tl.bn1;
     for (int c = tid; c < C; c += blockDim.x) coef[c] = a.g1[c] * (float)(1.0 / sqrt(bn1[C + c] + (double)a.eps));
@@ -651,8 +706,10 @@ __global__ void __launch_bounds__(256) train_back2_kernel(TrainArgs a) {
         zb[tid] = rows_loc > 0.0 ? (float)(a.st[a.tl.mom1 + tid] / rows_loc) : 0.f;
     }
     for (int i = tid; i < 32 * 64; i += blockDim.x) Qh[i] = (float)kq[64 + 32 * 64 + i];
-    for (int i = tid; i < 320; i += blockDim.x) accd[i] = 0.0;
     const int j = tid & 31, mg = tid >> 5;  // column of the x0 half, one of 8 row / channel groups
+    float db = 0.f, dg = 0.f, a0r[8];      // dbeta0[j], dgamma0[j], A0[j][:] over this thread's rows of this CTA's pillars
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0r[i] = 0.f;
     float q[64];  // row j of Q
 #pragma unroll
     for (int i = 0; i < 64; ++i) q[i] = (float)kq[64 + j * 64 + i];
@@ -682,19 +739,40 @@ __global__ void __launch_bounds__(256) train_back2_kernel(TrainArgs a) {
         if (tid + 256 < C) { dus[tid + 256] = coef[tid + 256] * du1; ams[tid + 256] = am1; }
         decorate(a, p, slots_of(a, w.d0), w.q0, s);
         const int rows = layer0_rows<false>(a, p, s);
-        for (int i = tid; i < rows * 33; i += blockDim.x) G[i] = 0.f;
+        // The pillar's channels sorted by their winning row (counting sort; shared-memory float atomics are CAS loops, the
+        // integer ones are native): row m then sums its own list, G[m][:32] = sum_{c: m*_c = m} a1_c du_c W1[c][:32].
+        for (int i = tid; i <= rows; i += blockDim.x) hist[i] = 0;
+        if (tid < 32) dh[tid] = 0.f;
         __syncthreads();
-        float dhp = 0.f;  // sparse part of dh[j], summed over this thread's channels
+        int pos0 = -1, pos1 = -1;
         if (p.own) {
-            // sparse rows: G[m*_c][:32] += a1_c du_c W1[c][:32]; their hmax half only through its sum
+            if (tid < C && dus[tid] != 0.f) pos0 = atomicAdd(&hist[ams[tid]], 1);
+            if (tid + 256 < C && dus[tid + 256] != 0.f) pos1 = atomicAdd(&hist[ams[tid + 256]], 1);
+        }
+        __syncthreads();
+        if (tid < 32) {  // exclusive prefix of hist[0 .. rows] (lane = a run of consecutive rows)
+            const int per = (rows + 32) / 32, lo = tid * per, hi = min(lo + per, rows + 1);
+            int sum = 0;
+            for (int i = lo; i < hi; ++i) sum += hist[i];
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= o) inc += t;
+            }
+            int run = inc - sum;
+            for (int i = lo; i < hi; ++i) { const int h = hist[i]; hist[i] = run; run += h; }
+        }
+        __syncthreads();
+        if (pos0 >= 0) order[hist[ams[tid]] + pos0] = tid;
+        if (pos1 >= 0) order[hist[ams[tid + 256]] + pos1] = tid + 256;
+        float dhp = 0.f;  // sparse part of dh[j]: the hmax half of the sparse rows enters only through its sum
+        if (p.own) {
             for (int c = mg; c < C; c += 8) {
                 const float v = dus[c];
-                if (v == 0.f) continue;
-                atomicAdd(&G[(size_t)ams[c] * 33 + j], v * __ldg(a.W1 + (size_t)c * 64 + j));
-                dhp = __fmaf_rn(v, __ldg(a.W1 + (size_t)c * 64 + 32 + j), dhp);
+                if (v != 0.f) dhp = __fmaf_rn(v, __ldg(a.W1 + (size_t)c * 64 + 32 + j), dhp);
             }
         }
-        if (tid < 32) dh[tid] = 0.f;
         __syncthreads();
         atomicAdd(&dh[j], dhp);
         // dz[m][j] = G[m][j] + w_m (kvec'[j] - sum_i Q[j][i] (z[m][i] - zbar[i])); row n carries all M - n padded slots
@@ -711,8 +789,14 @@ __global__ void __launch_bounds__(256) train_back2_kernel(TrainArgs a) {
                 acc = __fmaf_rn(q[i4 * 4 + 0], x.x - z.x, acc); acc = __fmaf_rn(q[i4 * 4 + 1], x.y - z.y, acc);
                 acc = __fmaf_rn(q[i4 * 4 + 2], x.z - z.z, acc); acc = __fmaf_rn(q[i4 * 4 + 3], x.w - z.w, acc);
             }
+            float gs = 0.f;
+            const int t1 = hist[m + 1];
+            for (int t = hist[m]; t < t1; ++t) {
+                const int c = order[t];
+                gs = __fmaf_rn(dus[c], __ldg(a.W1 + (size_t)c * 64 + j), gs);
+            }
             const float wt = (m < p.n) ? 1.f : (float)(M - p.n);
-            G[(size_t)m * 33 + j] += wt * (kv[j] - acc);
+            G[(size_t)m * 33 + j] = gs + wt * (kv[j] - acc);
         }
         if (mg == 0) {  // dense part of dh[j]: M kvec'[32 + j] - Q[32 + j, :] . (sum over the slots of z - M zbar)
             const float fm = (float)M;
@@ -726,9 +810,6 @@ __global__ void __launch_bounds__(256) train_back2_kernel(TrainArgs a) {
         }
         __syncthreads();
         {
-            float db = 0.f, dg = 0.f, a0r[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a0r[i] = 0.f;
             const int arg = s.am0[j];
             const float dhk = dh[j];
             for (int m = mg; m < rows; m += 8) {
@@ -751,17 +832,22 @@ __global__ void __launch_bounds__(256) train_back2_kernel(TrainArgs a) {
                 }
                 dg = __fmaf_rn(dx, yh, dg);
             }
-            atomicAdd(&accd[j], (double)db);
-            atomicAdd(&accd[32 + j], (double)dg);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(&accd[64 + j * 8 + i], (double)a0r[i]);
         }
         __syncthreads();
     }
-    double* back0 = a.st + a.tl.back0;
-    double* A0 = a.st + a.tl.A0;
-    if (tid < 64) atomicAdd(back0 + tid, accd[tid]);
-    atomicAdd(A0 + tid, accd[64 + tid]);
+    accf[(mg * 32 + j) * 10 + 0] = db;
+    accf[(mg * 32 + j) * 10 + 1] = dg;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) accf[(mg * 32 + j) * 10 + 2 + i] = a0r[i];
+    __syncthreads();
+    for (int e = tid; e < 320; e += blockDim.x) {  // e = column * 10 + field: merge the 8 row groups in float64
+        double t = 0.0;
+        for (int g8 = 0; g8 < 8; ++g8) t += (double)accf[(g8 * 32 + e / 10) * 10 + e % 10];
+        const int k = e / 10, f = e % 10;
+        if (f == 0) atomicAdd(a.st + a.tl.back0 + k, t);
+        else if (f == 1) atomicAdd(a.st + a.tl.back0 + 32 + k, t);
+        else atomicAdd(a.st + a.tl.A0 + k * 8 + (f - 2), t);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -842,8 +928,8 @@ int64_t p3p_pfn_train_state_doubles(int32_t channels, int64_t* offsets) {
     if (channels < 1 || channels > 512) return 0;
     const TrainLayout l = make_train_layout(channels);
     if (offsets) {
-        const int64_t o[13] = {l.mom0, l.sums0, l.bn0, l.mom1, l.sums1, l.bn1, l.back1, l.back1g, l.A1, l.kq, l.back0, l.back0g, l.A0};
-        for (int i = 0; i < 13; ++i) offsets[i] = o[i];
+        const int64_t o[14] = {l.mom0, l.sums0, l.bn0, l.mom1, l.sums1, l.bn1, l.cen, l.back1, l.back1g, l.A1, l.kq, l.back0, l.back0g, l.A0};
+        for (int i = 0; i < 14; ++i) offsets[i] = o[i];
     }
     return l.total;
 }
@@ -884,9 +970,15 @@ int p3p_pfn_train_stats1(const p3p_grid* grid, int32_t num_tiles, int64_t total_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     train_bn_kernel<<<1, 32, 0, st>>>(state + a.tl.sums0, 32, state + a.tl.bn0, nullptr, nullptr);
     const size_t smem = smem_floats(a.g.M, false) * 4;
-    rc = opt_in(train_stats1_kernel, smem + 64 * 32 * sizeof(double));
+    rc = opt_in(train_stats1_kernel, smem + 64 * sizeof(float));
     if (rc) return rc;
-    if (num_tiles > 0) train_stats1_kernel<<<grid_size(num_tiles, a.g.Vmax, 2), 256, smem + 64 * 32 * sizeof(double), st>>>(a);
+    rc = opt_in(train_centre_kernel, smem);
+    if (rc) return rc;
+    if (num_tiles > 0) {
+        train_centre_kernel<<<kCentreCtas, 256, smem, st>>>(a);
+        train_stats1_kernel<<<grid_size(num_tiles, a.g.Vmax, 3), 256, smem + 64 * sizeof(float), st>>>(a);
+        train_uncentre_kernel<<<1, 1024, 0, st>>>(a);
+    }
     const double* mom = state + a.tl.mom1;
     train_sums_kernel<<<a.C, 64, 0, st>>>(a.W1, a.C, 64, mom, mom + 64, state + a.tl.mom0, state + a.tl.sums1);
     P3P_CUDA_CHECK(cudaGetLastError());
@@ -963,7 +1055,7 @@ int p3p_pfn_backward2(const p3p_grid* grid, int32_t num_tiles, int64_t total_poi
     train_kq_kernel<<<65, 64, (size_t)a.C * sizeof(double), st>>>(a);
     train_kq2_kernel<<<1, 64, 0, st>>>(a);
     const size_t fl = smem_floats(a.g.M, false) + (size_t)(a.g.M + 1) * 33 + 3 * (size_t)a.C + 32 + 64 + 64 + 32 * 64;
-    const size_t smem = fl * 4 + 8 + 320 * sizeof(double);  // (+ 8: the double accumulators behind the floats are re-aligned)
+    const size_t smem = (fl + 8 * 32 * 10 + a.g.M + 2 + a.C) * 4;
     rc = opt_in(train_back2_kernel, smem);
     if (rc) return rc;
     if (num_tiles > 0) train_back2_kernel<<<grid_size(num_tiles, a.g.Vmax, 2), 256, smem, st>>>(a);

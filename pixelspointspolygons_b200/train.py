@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from . import _lib
 
-_STATE_FIELDS = ("mom0", "sums0", "bn0", "mom1", "sums1", "bn1", "back1", "back1g", "A1", "kq", "back0", "back0g", "A0")
+_STATE_FIELDS = ("mom0", "sums0", "bn0", "mom1", "sums1", "bn1", "cen", "back1", "back1g", "A1", "kq", "back0", "back0g", "A0")
 
 
 def state_layout(channels: int):

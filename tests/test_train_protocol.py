@@ -119,7 +119,7 @@ def test_state_layout_matches_the_header():
     total, offs = p3p_train.state_layout(384)
     keys = list(offs)
     assert keys == list(p3p_train._STATE_FIELDS) and offs["mom0"] == 0
-    sizes = dict(mom0=73, sums0=65, bn0=64, mom1=64 + 4096, sums1=769, bn1=768, back1=768, back1g=768, A1=384 * 64, kq=64 + 4096,
+    sizes = dict(mom0=73, sums0=65, bn0=64, mom1=64 + 4096, sums1=769, bn1=768, cen=65, back1=768, back1g=768, A1=384 * 64, kq=64 + 4096,
                  back0=64, back0g=64, A0=256)
     for a, b in zip(keys[:-1], keys[1:]):
         assert offs[b] - offs[a] >= sizes[a] and offs[a] % 2 == 0
