@@ -471,6 +471,49 @@ def sub_result(dev, rank, workload, precision, B, N, M, seconds=0.4):
                 "max_points_per_voxel": M, "error": repr(e)[:300]}
 
 
+def train_sub_result(dev, rank, B, N, M, with_dense):
+    """The optional training step: forward + backward of the LiDAR encoder in train mode through the fused
+    kernels (pixelspointspolygons_b200/train.py), device-timed; next to it, on one GPU, the dense autograd formulation the
+    reference runs (nn.Linear + BatchNorm1d + ReLU + max over (V, M, *) tensors) on the same pillars."""
+    try:
+        from pixelspointspolygons_b200 import PointPillarsEncoder, default_cfg
+        from tools.synth import synth_tile, synth_weights
+
+        enc = PointPillarsEncoder(default_cfg(device=str(dev), max_num_points_per_voxel=M),
+                                  voxel_encoder={"in_channels": 3, "feat_channels": [64, 384]},
+                                  scatter={"in_channels": 384, "output_shape": [28, 28]}).to(dev).train()
+        enc.load_state_dict(synth_weights(0)[0])
+        x = torch.from_numpy(np.stack([synth_tile(N, 1000 * (rank + 1) + i, clustered=(i % 2 == 1)) for i in range(B)])).to(dev)
+        wgt = torch.randn(B, 784, 384, device=dev)
+
+        def timed(fn, warm, iters):
+            def step():
+                enc.zero_grad(set_to_none=True)
+                (fn(x) * wgt).sum().backward()
+            for _ in range(warm):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(iters):
+                step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / iters
+
+        fused = timed(lambda t: enc(t), 3, 30)
+        out = {"workload": "train_step", "what": "forward + backward of the LiDAR encoder in train mode (BatchNorm batch statistics, "
+               "gradients of the six PFN parameters), exact fp32, eager launches", "tiles_per_gpu": B, "points_per_tile": N,
+               "max_points_per_voxel": M, "ms_per_step": fused, "tiles_per_s_per_gpu": B / (fused * 1e-3)}
+        if with_dense:
+            out["dense_autograd_ms_per_step"] = timed(lambda t: enc.forward_dense_reference(t), 1, 3)
+        del enc, x, wgt
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:
+        return {"workload": "train_step", "tiles_per_gpu": B, "points_per_tile": N, "max_points_per_voxel": M, "error": repr(e)[:300]}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -733,6 +776,8 @@ def main():
                 continue
             barrier()
             subs.append(sub_result(dev, rank, wl, prec, b, n, m))
+        barrier()
+        subs.append(train_sub_result(dev, rank, 16, N, M, with_dense=(world == 1)))
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
