@@ -747,7 +747,7 @@ def main():
         pass
     pfn_s = (stage_ms["pfn"] or 0.0) * 1e-3
     achieved_tf = flops / pfn_s / 1e12 if pfn_s > 0 else None
-    roofline = {"kernel": "pfn_tc_kernel" if (args.precision != "fp32" and M <= 64) else "pfn_simt_kernel",
+    roofline = {"kernel": "pfn_tc_kernel" if (args.precision != "fp32" and M <= 512) else "pfn_simt_kernel",
                 "bound": "tensor", "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": (achieved_tf / tensor_peak) if achieved_tf else None, "traffic": traffic,
                 "traffic_source": traffic_src,
