@@ -103,12 +103,12 @@ int make_ws_layout(const GridDev& g, int B, int64_t total_points, WsLayout* out)
     WsLayout l;
     memset(&l, 0, sizeof(l));
     l.B = B;
-    const int target = 3 * device_sm_count();
+    const int target = kVoxCtasPerSm * device_sm_count();
     int64_t denom = target - B;
     if (denom < 64) denom = 64;
     int64_t S = (total_points + denom - 1) / denom;
-    S = (S + 1023) / 1024 * 1024;  // every lane owns whole groups of 4 points
-    if (S < 1024) S = 1024;
+    S = (S + kChunkGranule - 1) / kChunkGranule * kChunkGranule;  // every lane owns whole groups of 4 points
+    if (S < kChunkGranule) S = kChunkGranule;
     if (S > kMaxChunkPoints) S = kMaxChunkPoints;
     l.chunk_points = (int)S;
     // chunks of a tile start at its first point rounded down to a multiple of 4: sum_b ceil((n_b + 3) / S) <= this

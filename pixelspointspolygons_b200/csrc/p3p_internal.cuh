@@ -25,7 +25,20 @@ int fail(int code, const char* fmt, ...);
 // ----------------------------------------------------------------------------------------------
 constexpr int kFlagDropOverflow = P3P_GRID_DROP_OVERFLOW;  // DESIGN.md uncertainty ledger U1
 constexpr int kMaxKeys = 6144;        // smem histogram budget of the ranking kernels
-constexpr int kMaxChunkPoints = 4096; // points per ranking chunk held in registers (16 per lane x 256 threads)
+// voxelizer shape (build-time tunables): threads per CTA, CTAs per SM, points per lane; a chunk holds threads * points-per-lane
+// points and the whole batch should be ONE wave of CTAs (capi.cu sizes the chunks for that)
+#ifndef P3P_VOX_THREADS
+#define P3P_VOX_THREADS 256
+#endif
+#ifndef P3P_VOX_CTAS
+#define P3P_VOX_CTAS 3
+#endif
+#ifndef P3P_VOX_PPL
+#define P3P_VOX_PPL 16
+#endif
+constexpr int kVoxThreads = P3P_VOX_THREADS, kVoxCtasPerSm = P3P_VOX_CTAS;
+constexpr int kChunkGranule = 4 * kVoxThreads;                  // every lane owns whole groups of 4 points
+constexpr int kMaxChunkPoints = kVoxThreads * P3P_VOX_PPL;      // points per ranking chunk held in registers
 constexpr int kC0 = 32;               // feat_channels[0] / 2: width of PFN layer 0
 
 struct GridDev {
@@ -49,7 +62,7 @@ int make_grid(const p3p_grid* g, GridDev* out);
 // ----------------------------------------------------------------------------------------------
 struct WsLayout {
     int B;
-    int chunk_points;      // S: points per ranking chunk (multiple of 1024, <= kMaxChunkPoints)
+    int chunk_points;      // S: points per ranking chunk (multiple of kChunkGranule, <= kMaxChunkPoints)
     int max_chunks;        // upper bound of the number of chunks over the batch (= grid of the voxelize kernel)
     int key_stride;        // chunk_hist row stride (elements)
     size_t off_sync;       // uint32 ticket, flags[max_chunks], tile_done[B], tile_sat[B], then uint8 edge[B][num_keys]

@@ -55,7 +55,7 @@ extern "C" int p3p_debug_timeline(unsigned long long* host, int ctas) {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = kVoxThreads;  // (build-time tunable, p3p_internal.cuh)
 constexpr int kWarps = kThreads / 32;
 constexpr int kIters = kMaxChunkPoints / kThreads;  // points per lane held in registers
 
@@ -321,7 +321,7 @@ constexpr unsigned kCrossFlag = 0x8000u;   // base_s entry: the key crosses M in
 //                       index threshold exactly; survivors take the slots [pre, M) in arbitrary order.
 // No step of this depends on the order in which the hardware serves same-address atomics.
 template <bool kFast>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, kVoxCtasPerSm)
 voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __restrict__ offsets, int B, GridDev g, int S, WsPtrs ws, int32_t* __restrict__ point_hash, int need_plan, int pdl_from) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = g.num_keys;
@@ -721,15 +721,15 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
                 float4 v[2][3];
 #pragma unroll
                 for (int g2 = 0; g2 < 2; ++g2) {
-                    if ((live >> (h + g2)) & 1u) {
+                    if (h + g2 < kGroups && ((live >> (h + g2)) & 1u)) {
 #pragma unroll
                         for (int u = 0; u < 3; ++u) v[g2][u] = __ldg(q + (size_t)(h + g2) * (kThreads * 3) + u);
                     }
                 }
 #pragma unroll
                 for (int g2 = 0; g2 < 2; ++g2) {
-                    const int gi = h + g2;
-                    if ((live >> gi) & 1u) {
+                    const int gi = (h + g2 < kGroups) ? h + g2 : kGroups - 1;
+                    if (h + g2 < kGroups && ((live >> gi) & 1u)) {
                         const float4 a = v[g2][0], b = v[g2][1], c = v[g2][2];
                         const float x[4] = {a.x, a.w, b.z, c.y}, y[4] = {a.y, b.x, b.w, c.z}, z[4] = {a.z, b.y, c.x, c.w};
 #pragma unroll
