@@ -365,6 +365,9 @@ class PointPillarsEncoder(nn.Module):
         from .train import FusedPFNTrain
         values, offsets, B = self._pack(x_lidar)
         l0, l1 = self.voxel_encoder.pfn_layers[0], self.voxel_encoder.pfn_layers[1]
+        if not (l0.norm.training and l1.norm.training):
+            raise NotImplementedError("train() with a BatchNorm layer of the PillarFeatureNet switched to eval(): the training "
+                                      "kernels normalise both layers with batch statistics; call .eval() on the encoder to freeze it")
         x = FusedPFNTrain.apply(self, values, offsets, B, l0.linear.weight, l0.norm.weight,
                                 l0.norm.bias, l1.linear.weight, l1.norm.weight, l1.norm.bias)
         if return_flattened:

@@ -161,7 +161,8 @@ class FusedPFNTrain(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        ctx.p3p.out = ctx.saved_tensors[0]
-        grads = train_backward(ctx.p3p, grad_out)
-        ctx.p3p = None
+        c = ctx.p3p  # (kept: with retain_graph=True the node may run again; every pass re-zeroes its accumulators)
+        c.out = ctx.saved_tensors[0]
+        grads = train_backward(c, grad_out)
+        c.out = None
         return (None, None, None, None, *grads)

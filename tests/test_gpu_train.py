@@ -121,6 +121,15 @@ def test_training_nchw_view_and_second_step(cuda_device):
     with torch.no_grad():  # train mode without autograd: batch statistics, no graph
         o = enc(x)
     assert not o.requires_grad
+    enc.zero_grad()
+    out = enc(x)
+    out.sum().backward(retain_graph=True)  # the node may run twice
+    g_once = enc.voxel_encoder.pfn_layers[0].linear.weight.grad.clone()
+    out.sum().backward()
+    assert rel(enc.voxel_encoder.pfn_layers[0].linear.weight.grad, 2 * g_once) <= 1e-5
+    enc.voxel_encoder.pfn_layers[0].norm.eval()
+    with pytest.raises(NotImplementedError):
+        enc(x)
 
 
 def test_training_two_simulated_ranks_match_whole_batch(cuda_device):
