@@ -1,0 +1,14 @@
+#!/bin/bash
+# what the driver runs at round end, in its order: GPU tests, smoke(), reference arm, own arm (1 GPU)
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -n 3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -n 5 gpurun_out/smoke.log
+( time timeout 900 python bench.py --impl reference --gpus 1 --steps 5 --warmup 3 > gpurun_out/bench_final_ref.json 2> gpurun_out/bench_final_ref.err ) 2>&1 | grep real; echo "reference arm exit $?"
+( time timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err ) 2>&1 | grep real; echo "bench exit $?"
+python - <<'PY'
+import json
+r=json.loads(open("gpurun_out/bench_final_ref.json").read().strip().splitlines()[-1])
+d=json.loads(open("gpurun_out/bench_final.json").read().strip().splitlines()[-1])
+print("reference", round(r["value"],2), r["unit"], r["cpu_baseline"]["cores"], "cores |", "ours", round(d["value"]), "e2e", round(d["e2e"]["value"]), "ratio e2e", round(d["e2e"]["value"]/r["value"]), "roofline", round(d["roofline"]["frac"],3), "hbm", round(d["hbm_roofline"]["frac"],3), "launches", d["gpu_launches"], d["clocks"], d["cpu_baseline"])
+PY
