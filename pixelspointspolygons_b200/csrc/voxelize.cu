@@ -303,7 +303,10 @@ constexpr unsigned kKeyMask = (1u << kKeyBits) - 1u;
 static_assert(kMaxKeys <= (1 << kKeyBits), "key field too narrow");
 static_assert(kMaxChunkPoints * 8 < 65536, "8 chunk rows must add up inside 16-bit lanes");
 constexpr int kGroups = kIters / 4;        // groups of 4 consecutive points (48 bytes = 3 x 16-byte loads) per thread
-constexpr int kCrossBatch = 256;           // crossing keys resolved per round
+#ifndef P3P_CROSS_BATCH
+#define P3P_CROSS_BATCH 256
+#endif
+constexpr int kCrossBatch = P3P_CROSS_BATCH;  // crossing keys resolved per round (512 measured: slower, the larger scratch costs L1)
 constexpr int kCells = kGroups * kWarps;   // the chunk-local order is (group, warp, lane, e): 32 cells (group, warp) of 128 consecutive points
 static_assert(kMaxChunkPoints / kCells <= 255, "points of a cell must fit the 8-bit fields of the boundary word");
 constexpr unsigned kCrossFlag = 0x8000u;   // base_s entry: the key crosses M inside this chunk; low 15 bits = crossing id
@@ -638,18 +641,18 @@ voxelize_kernel(const float* __restrict__ pts, int stride_arg, const int64_t* __
             }
         }
         __syncthreads();
-        if (tid < nb) {  // exclusive prefix over the 32 cells (conflict-free: ids are the fast index), boundary cell
-            const unsigned need = need_s[c0 + tid];
+        for (int id = tid; id < nb; id += kThreads) {  // exclusive prefix over the cells (conflict-free: ids are the fast index), boundary cell
+            const unsigned need = need_s[c0 + id];
             unsigned P = 0, bnd = 0;
             bool found = false;
 #pragma unroll 8
             for (int c = 0; c < kCells; ++c) {
-                const unsigned v = cell_s[c * kCrossBatch + tid];
-                cell_s[c * kCrossBatch + tid] = (uint16_t)P;
+                const unsigned v = cell_s[c * kCrossBatch + id];
+                cell_s[c * kCrossBatch + id] = (uint16_t)P;
                 if (!found && P + v >= need) { found = true; bnd = (unsigned)c | ((need - P) << 8) | (v << 16); }
                 P += v;
             }
-            bnd_s[tid] = bnd;  // cell | survivors inside it << 8 | its points of the key << 16
+            bnd_s[id] = bnd;  // cell | survivors inside it << 8 | its points of the key << 16
         }
         __syncthreads();
         if (__any_sync(0xffffffffu, bmask != 0)) {

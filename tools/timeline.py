@@ -52,3 +52,12 @@ for i, nm in enumerate(names):
         if both.sum():
             line += f"   | phase: p10={np.percentile(d, 10):6.2f} p50={np.median(d):6.2f} p90={np.percentile(d, 90):6.2f} max={d.max():6.2f}"
     print(line)
+
+# per chunk index inside the tile (slot 12 = chunk + 1, slot 13 = tile + 1): where the tail of the kernel comes from
+if t.shape[1] > 13 and (t[:, 12] > 0).any():
+    print("chunk: CTAs | end of phase, median over the tiles (us): located hashed counted published acquired classified scattered crossing synced | slowest end")
+    for c in sorted(set(int(v) for v in t[:, 12] if v > 0)):
+        rows = t[t[:, 12] == c]
+        ends = [(np.median((rows[:, i][rows[:, i] > 0] - t0) / 1e3) if (rows[:, i] > 0).any() else float("nan")) for i in range(1, 10)]
+        last = max(((rows[:, i][rows[:, i] > 0] - t0) / 1e3).max() for i in range(1, 10) if (rows[:, i] > 0).any())
+        print(f"  c={c - 1:3d} n={len(rows):3d} | " + " ".join(f"{e:6.2f}" for e in ends) + f" | {last:6.2f}")
