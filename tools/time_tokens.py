@@ -4,7 +4,7 @@ import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import pillars_oracle as po
+from tools import synth as po  # (neutral generators: measurement tools do not touch oracle/)
 from pixelspointspolygons_b200 import PointPillarsEncoder, default_cfg
 dev = torch.device("cuda:0")
 enc = PointPillarsEncoder(default_cfg(device="cuda:0"), voxel_encoder={"in_channels": 3, "feat_channels": [64, 384]},

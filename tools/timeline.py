@@ -10,7 +10,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import pillars_oracle as po
+from tools import synth as po  # (neutral generators: measurement tools do not touch oracle/)
 from pixelspointspolygons_b200 import PointPillarsEncoder, _lib, default_cfg
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
