@@ -12,3 +12,7 @@ r=json.loads(open("gpurun_out/bench_final_ref.json").read().strip().splitlines()
 d=json.loads(open("gpurun_out/bench_final.json").read().strip().splitlines()[-1])
 print("reference", round(r["value"],2), r["unit"], r["cpu_baseline"]["cores"], "cores |", "ours", round(d["value"]), "e2e", round(d["e2e"]["value"]), "ratio e2e", round(d["e2e"]["value"]/r["value"]), "roofline", round(d["roofline"]["frac"],3), "hbm", round(d["hbm_roofline"]["frac"],3), "launches", d["gpu_launches"], d["clocks"], d["cpu_baseline"])
 PY
+# per-chunk voxelizer timeline (variant build on the box)
+mkdir -p pixelspointspolygons_b200/variants
+python tools/build_variant.py tl -DP3P_TIMELINE > gpurun_out/build_tl.log 2>&1 || tail gpurun_out/build_tl.log
+P3P_LIB=$PWD/pixelspointspolygons_b200/variants/libp3p_tl.so timeout 120 python tools/timeline.py 16 100000 > gpurun_out/vox_tl_chunks.txt 2>&1; echo "timeline exit $?"
