@@ -13,11 +13,13 @@
 //         = relu(max_p(W1a' h_p) + W1b' hmax + b1)  (relu and "+ const" are monotone; the BN scale is already
 //                                                    inside W1a', so its sign does not matter)
 //
-// pfn_tc_kernel (M <= 64, C <= 384): persistent warp-specialised pipeline, described at the kernel.
-// The decorated (V, M, 8) tensor and every (V, M, *) intermediate of the reference never exist in HBM.
+// pfn_tc_kernel (M <= 512 as 1 / 2 / 4 / 8 blocks of 64 rows per pillar, C <= 384): persistent warp-specialised pipeline,
+// described at the kernel.  The decorated (V, M, 8) tensor and every (V, M, *) intermediate of the reference never exist
+// in HBM.
 //
 // pfn_simt_kernel: exact fp32 FMA, literal 8-channel formulation, any M and C -- the GPU-side cross-check of the
-// tensor-core path and the route for configurations the tensor-core kernel does not cover (density ablation).
+// tensor-core path, the P3P_PRECISION_FP32 route, and the route for configurations the tensor-core kernel does not cover
+// (M > 512, C > 384).  The training step (batch statistics, backward) lives in pfn_train.cu.
 #include <cuda_fp16.h>
 
 #include "p3p_internal.cuh"
@@ -488,7 +490,7 @@ __device__ __forceinline__ float max16(const float (&v)[16]) {
     for (int i = 0; i < 5; ++i) r[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
     return fmax3(fmax3(r[0], r[1], r[2]), fmaxf(r[3], r[4]), v[15]);
 }
-// pfn_tc_kernel (M <= 64, C <= 384): per CTA a persistent pipeline
+// pfn_tc_kernel (C <= 384; M <= 64 per 64-row block, larger M as 2 / 4 / 8 blocks in mode 0): per CTA a persistent pipeline
 //   8 front-end warps  : warp w takes item w of every unit (8 consecutive items); layer 0 in its affine form
 //                        W0' d_p + b0 = Ux x' + Uy y' + Uz z + kappa(pillar)   (x' = x - centre_x, ...)
 //                        -> 3 FMA per (point, channel); 16-byte row chunks written (tf32 / 16-bit) straight into the
