@@ -396,6 +396,9 @@ static_assert(!P3P_EPI4 || 4 * kRegMma + 8 * kRegFront + 16 * kRegEpi4 <= 28 * 7
 #ifndef P3P_EPI_PIPE
 #define P3P_EPI_PIPE 0
 #endif
+#ifndef P3P_EPI_UNROLL
+#define P3P_EPI_UNROLL 1  // the unit's 4 pairs unrolled: barrier parities and strip offsets become constants of the body (r02: PFN 42.2 -> 41.1 us)
+#endif
 #ifndef P3P_EPI_DEFER
 #define P3P_EPI_DEFER 0
 #endif
@@ -489,6 +492,12 @@ __device__ __forceinline__ float max16(const float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 5; ++i) r[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
     return fmax3(fmax3(r[0], r[1], r[2]), fmaxf(r[3], r[4]), v[15]);
+}
+// the same with a running maximum folded in: 17 values, still 8 three-input maxima
+__device__ __forceinline__ float max16_with(float prev, const float (&v)[16]) {
+    const float r0 = fmax3(prev, v[0], v[1]), r1 = fmax3(v[2], v[3], v[4]), r2 = fmax3(v[5], v[6], v[7]);
+    const float r3 = fmax3(v[8], v[9], v[10]), r4 = fmax3(v[11], v[12], v[13]);
+    return fmax3(fmax3(r0, r1, r2), fmax3(r3, r4, v[14]), v[15]);
 }
 // pfn_tc_kernel (C <= 384; M <= 64 per 64-row block, larger M as 2 / 4 / 8 blocks in mode 0): per CTA a persistent pipeline
 //   8 front-end warps  : warp w takes item w of every unit (8 consecutive items); layer 0 in its affine form
@@ -1199,11 +1208,19 @@ __global__ void __launch_bounds__(kThreadsOf<kMode>, 1) pfn_tc_kernel(PfnArgs a)
             // for the unit's W1b' hmax term in a per-warp shared-memory strip, not in registers).  Four loads of 16
             // columns per pillar through two register buffers: the arithmetic on one buffer overlaps the load into the
             // other.
+#if P3P_EPI_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int pr = 0; pr < kPairsPerUnit; ++pr) {
 #pragma unroll
                 for (int s = 0; s < kAccStages; ++s, ++jn) {
+#if P3P_EPI_UNROLL
+                    const uint32_t tph = (uint32_t)pr & 1u;  // jn = 8 j + 2 pr + s: (jn >> 1) & 1 is a constant of the unrolled body
+#else
                     const uint32_t tph = (uint32_t)(jn >> 1) & 1u;
+#endif
                     if (quad == 0) PTL(9 + g, jn, 0);
                     if (!inflight) {
                         if (!ready) mbar_wait_sa(tf_sa + 8u * s, tph);
@@ -1213,14 +1230,19 @@ __global__ void __launch_bounds__(kThreadsOf<kMode>, 1) pfn_tc_kernel(PfnArgs a)
                     if (quad == 0) PTL(9 + g, jn, 1);
                     tmem_ld_wait16(va);
                     tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 16), vb);
+#if P3P_EPI_UNROLL
+                    // (inside a unit the next pillar always exists; behind its last pillar only if another unit follows)
+                    ready = (2 * pr + s + 1 < kUnit || j + 1 < my_units_g) ? mbar_test_sa(tf_sa + 8u * (s ^ 1), (uint32_t)((2 * pr + s + 1) >> 1) & 1u) : 0u;
+#else
                     ready = (jn + 1 < my_pillars) ? mbar_test_sa(tf_sa + 8u * (s ^ 1), (uint32_t)((jn + 1) >> 1) & 1u) : 0u;
+#endif
                     const float r0 = max16(va);
                     tmem_ld_wait16(vb);
                     tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 32), va);
-                    const float r1 = max16(vb);
+                    const float r1 = max16_with(r0, vb);
                     tmem_ld_wait16(va);
                     tmem_ld16_issue(taddr_o + (uint32_t)(s * kAccCols + 48), vb);
-                    const float r2 = max16(va);
+                    const float r2 = max16_with(r1, va);
                     tmem_ld_wait16(vb);
                     tc_fence_before();
                     mbar_arrive_sa(te_sa + 8u * s);
@@ -1233,7 +1255,7 @@ __global__ void __launch_bounds__(kThreadsOf<kMode>, 1) pfn_tc_kernel(PfnArgs a)
                         tmem_ld16_issue(taddr_o + (uint32_t)((s ^ 1) * kAccCols), va);
                     }
 #endif
-                    sts_f32(rmax_sa + (uint32_t)((j & 1) * (kUnit * 128) + (2 * pr + s) * 128), fmaxf(fmax3(r0, r1, r2), max16(vb)));
+                    sts_f32(rmax_sa + (uint32_t)((j & 1) * (kUnit * 128) + (2 * pr + s) * 128), max16_with(r2, vb));
                     if (quad == 0) PTL(9 + g, jn, 2);
                 }
                 // (P3P_EPI_DEFER: the PREVIOUS unit's tail runs here, after this unit's first pair)
