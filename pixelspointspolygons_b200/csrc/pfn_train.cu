@@ -13,13 +13,17 @@
 // Forward.  y is linear in its input, so the batch statistics follow from input moments:
 //     sum y_c = W_c . (sum in),   sum y_c^2 = W_c (sum in in^T) W_c^T
 // stats0: s = sum d, S = sum d d^T over the kept points (one pass over the slots);
-// stats1: sum z, Z = sum z z^T (64 x 64) with x0 from the layer-0 batch statistics (second pass).
+// stats1: sum z, Z = sum z z^T (64 x 64) with x0 from the layer-0 batch statistics (second pass), accumulated in fp32 about
+//         a sampled centre and merged / un-centred in float64 (the fp64 pipe of this GPU is ~1 lane per clock and SM).
 // Per-channel (sum y, sum y^2, rows) of each layer is what ranks exchange under SyncBatchNorm (65 and 2C + 1 values,
-// SURVEY 8e).  With the batch statistics known, BatchNorm is the same affine map as in eval mode: the output comes from
-// the inference kernels (pfn.cu) run on a blob prepared from the batch statistics.
+// SURVEY 8e).  With the batch statistics known, BatchNorm is the same affine map as in eval mode; the training forward
+// (train_forward_kernel, exact fp32, thread = channel) applies it and keeps the winning row of every (pillar, channel).
+// (The inference kernels of pfn.cu on a blob prepared from the batch statistics give the same output faster -- 
+// p3p_pfn_train_stats2 + p3p_pfn_prepare + p3p_encode_workspace -- but their tf32 / fp16 operand rounding is amplified by the
+// division by the batch's own standard deviation: 2e-3 of scale measured.)
 //
 // Backward (g = d loss / d out, zero for pillars that lost their canvas cell):
-//   pass 1, per pillar and channel c: the winning row m* (arg max, recomputed in fp32), du = g [x1* > 0];
+//   pass 1, per pillar and channel c: the winning row m* (kept by the forward), du = g [out > 0];
 //           dbeta1_c += du, dgamma1_c += du yh1*, A1[c, :] += du z*  (the sparse part of dW1); (m*, du) kept for pass 2.
 //   The BatchNorm backward makes dy1 dense: dy1 = a1 (du - dbeta1 / R - yh1 dgamma1 / R) with a1 = g1 rstd1, but
 //           dz = dy1 W1 = G + kvec - Q z,    G = sparse rows, kvec (64), Q (64 x 64) batch constants,
