@@ -201,6 +201,10 @@ __global__ void __launch_bounds__(kPeThreads, 1) patch_embed_tc_kernel(PeArgs a)
     int round = 0;
     for (int mt0 = 0; mt0 < MT; mt0 += kTilesResident, ++round) {
         const int ntiles = (MT - mt0 < kTilesResident) ? MT - mt0 : kTilesResident;
+        // A further round (tf32: one resident tile) refills the weight tile's space, which the previous round's epilogue uses
+        // as its transpose staging: every warp must be through with it first.  (Found by running the suite under
+        // compute-sanitizer, whose timing let warp 0's bulk copy land under the other warps' staged values.)
+        if (round > 0) __syncthreads();
         if (prepared) {
             // the tiles are stored as their shared-memory operand images: one bulk copy per tile (TMA, no register
             // traffic) next to the threads' work on the pixel runs
